@@ -1,0 +1,74 @@
+"""ctypes binding of libctrlora_b200.so (the C ABI declared in include/ctrlora_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this module raises.
+"""
+import ctypes as C
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libctrlora_b200.so")
+_lib = None
+
+c_void_p, c_int, c_ll, c_float = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `struct ctrlora_gemm_args`."""
+    _fields_ = [
+        ("a", c_void_p), ("a_b", c_int), ("a_h", c_int), ("a_w", c_int), ("a_c", c_int), ("a_ld", c_ll),
+        ("w", c_void_p), ("kh", c_int), ("kw", c_int), ("pad", c_int),
+        ("a2", c_void_p), ("a2_c", c_int), ("a2_ld", c_ll), ("w2", c_void_p),
+        ("n", c_int), ("block_n", c_int), ("geglu", c_int),
+        ("out", c_void_p * 3), ("seg_width", c_int), ("transposed", c_int * 3),
+        ("ldc", c_int), ("out_f32", c_int),
+        ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int),
+        ("residual", c_void_p), ("ldr", c_int), ("out_scale", c_float),
+        ("head_dim", c_int), ("tok_pad", c_int), ("bf16", c_int),
+    ]
+
+
+class CtrloraError(RuntimeError):
+    pass
+
+
+_STATUS = {1: "bad argument", 2: "CUDA error", 3: "tensor-map encode error", 4: "unsupported"}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (building is the job of ctrlora_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise CtrloraError(
+                f"{_LIB_PATH} is missing: run `python -m ctrlora_b200.build` (needs nvcc). "
+                "ctrlora_b200 has no CPU or PyTorch fallback.")
+        _lib = C.CDLL(_LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(lib):
+    lib.ctrlora_abi_version.restype = c_int
+    lib.ctrlora_last_cuda_error.restype = C.c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("ctrlora_abi_version", "ctrlora_last_cuda_error"):
+            fn.restype = c_int
+
+
+def check(status, what):
+    if status != 0:
+        err = load().ctrlora_last_cuda_error()
+        raise CtrloraError(f"{what} failed: {_STATUS.get(status, status)} ({err.decode() if err else ''})")
+
+
+# Every symbol include/ctrlora_b200.h declares (tests/test_abi.py checks the two lists agree).
+EXPORTS = [
+    "ctrlora_abi_version",
+    "ctrlora_last_cuda_error",
+    "ctrlora_gemm_f16",
+    "ctrlora_gemm_f16_simt",
+]

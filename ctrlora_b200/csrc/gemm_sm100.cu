@@ -1,0 +1,404 @@
+// tcgen05 implicit-GEMM for sm_100a: one persistent, warp-specialised kernel that serves
+//   * every nn.Linear of the hot path            (reference: ldm/modules/attention.py:154-161, cldm/lora.py:285-291)
+//   * every 1x1 / 3x3 stride-1 Conv2d in NHWC    (reference: ldm/modules/diffusionmodules/openaimodel.py:162-274)
+// D[M, N] = sum_taps A_shifted[M, Cin] * W[N, tap, Cin]^T  (+ optional second 1x1 operand pair: the ResBlock skip conv)
+// A tiles are TMA boxes over the (C, W, H, B) activation tensor: a filter tap is a coordinate shift and the conv zero
+// padding is the TMA out-of-bounds fill, so no im2col buffer exists in HBM.  Accumulators live in TMEM (two 256-column
+// stages, so the epilogue of tile i overlaps the MMA main loop of tile i+1).
+#include "gemm_sm100.cuh"
+#include "ctrlora_b200.h"
+#include <stdio.h>
+#include <string.h>
+
+namespace ctrl {
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ GemmKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + GEMM_STAGES;
+    uint64_t* tfull = bars + 2 * GEMM_STAGES;
+    uint64_t* tempty = bars + 2 * GEMM_STAGES + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (p.kchunks2 > 0) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < GEMM_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int main_iters = p.taps * p.kchunks;
+    const int k_iters = main_iters + p.kchunks2;
+    const int bn_out = p.geglu ? (p.BN >> 1) : p.BN;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = GEMM_A_BYTES + p.BN * 128;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile % m_tiles, nt = tile / m_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.nb, n0 = nt * bn_out;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* a_dst = smem + stage * GEMM_STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + GEMM_A_BYTES;
+                    mbar_expect_tx(&full[stage], tx_bytes);
+                    if (it < main_iters) {
+                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                        const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
+                        tma_load_4d(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
+                        tma_load_3d(b_dst, &tmB, &full[stage], kc * GEMM_BK, tap, n0);
+                        if (p.geglu)
+                            tma_load_3d(b_dst + bn_out * 128, &tmB, &full[stage], kc * GEMM_BK, tap, p.N + n0);
+                    } else {
+                        const int kc = it - main_iters;
+                        tma_load_4d(a_dst, &tmA2, &full[stage], kc * GEMM_BK, w0, h0, b0);
+                        tma_load_3d(b_dst, &tmB2, &full[stage], kc * GEMM_BK, 0, n0);
+                    }
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer (single thread)
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int it = 0; it < k_iters; ++it) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + GEMM_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        umma_f16(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
+                                 p.idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ---------------------------------------------------- epilogue warps (TMEM -> registers -> global)
+        const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int r = lane_grp * 32 + lane;
+        const int iw = r % p.bw, ih = (r / p.bw) % p.bh, ib = r / (p.bw * p.bh);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile % m_tiles, nt = tile / m_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int gw = tw * p.bw + iw, gh = th * p.bh + ih, gb = tb * p.nb + ib;
+            const bool row_ok = gw < p.W && gh < p.H && gb < p.Bn;
+            const long long m = (static_cast<long long>(gb) * p.H + gh) * p.W + gw;
+            const int n0 = nt * bn_out;
+            const int img = row_ok ? static_cast<int>(m / p.rows_per_img) : 0;
+            const int tok = row_ok ? static_cast<int>(m % p.rows_per_img) : 0;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
+
+            for (int c = 0; c < bn_out; c += 32) {
+                uint32_t raw[32];
+                float v[32];
+                tmem_ld_32x32(t_row + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                const int nbase = n0 + c;
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
+                }
+                if (p.geglu) {
+                    uint32_t graw[32];
+                    tmem_ld_32x32(t_row + bn_out + c, graw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float g = __uint_as_float(graw[j]);
+                        if (p.bias && nbase + j < p.N) g += __ldg(p.bias + p.N + nbase + j);
+                        v[j] *= gelu_erf_f(g);
+                    }
+                }
+                if (row_ok) {
+                    if (p.rowbias) {
+                        const float* rb = p.rowbias + static_cast<long long>(img) * p.N + nbase;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < p.N) v[j] += __ldg(rb + j);
+                    }
+                    if (p.out_scale != 1.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+                    }
+                    const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
+                    if (p.residual) {
+                        const __half* rp = p.residual + m * p.ldr + nbase;
+                        if (full_chunk && (p.ldr & 7) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+                                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __half22float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x;
+                                    v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (c + j < bn_out && nbase + j < p.N) v[j] += __half2float(rp[j]);
+                        }
+                    }
+                    // ---- store
+                    int seg = 0, nloc = nbase;
+                    if (p.seg_width > 0) { seg = nbase / p.seg_width; nloc = nbase - seg * p.seg_width; }
+                    if (p.transposed[seg]) {
+                        __half* o = reinterpret_cast<__half*>(p.out[seg]) +
+                                    (static_cast<long long>(img) * p.seg_width + nloc) * p.tok_pad + tok;
+                        for (int j = 0; j < 32; ++j)
+                            if (c + j < bn_out && nbase + j < p.N) o[static_cast<long long>(j) * p.tok_pad] = __float2half_rn(v[j]);
+                    } else if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out[seg]) + m * p.ldc + nloc;
+                        if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (c + j < bn_out && nbase + j < p.N) o[j] = v[j];
+                        }
+                    } else {
+                        __half* o = reinterpret_cast<__half*>(p.out[seg]) + m * p.ldc + nloc;
+                        if (full_chunk && (p.ldc & 7) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u;
+                                u.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]);
+                                u.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
+                                u.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
+                                u.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
+                                reinterpret_cast<uint4*>(o)[q] = u;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (c + j < bn_out && nbase + j < p.N) o[j] = __float2half_rn(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// fp16 tensor map with SWIZZLE_128B, zero OOB fill; dims innermost first; strides (bytes) for dims 1..rank-1.
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) return CTRLORA_ERR_TMAP;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "ctrlora: cuTensorMapEncodeTiled failed (%d) rank %d dims", (int)r, rank);
+        for (int i = 0; i < rank; ++i) fprintf(stderr, " %llu", (unsigned long long)dims[i]);
+        fprintf(stderr, " box");
+        for (int i = 0; i < rank; ++i) fprintf(stderr, " %u", box[i]);
+        fprintf(stderr, "\n");
+        return CTRLORA_ERR_TMAP;
+    }
+    return CTRLORA_OK;
+}
+
+static int pow2_floor(int x) {
+    int p = 1;
+    while (p * 2 <= x) p *= 2;
+    return p;
+}
+
+static int g_num_sms = 0;
+static bool g_attr_set = false;
+
+}  // namespace ctrl
+
+using namespace ctrl;
+
+extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->a || !a->w || !a->out[0]) return CTRLORA_ERR_ARG;
+    if (a->a_c % 8 != 0 || a->a_ld % 8 != 0) return CTRLORA_ERR_ARG;
+    if (a->kh != a->kw || (a->kh != 1 && a->kh != 3)) return CTRLORA_ERR_UNSUPPORTED;
+    if (a->bf16) return CTRLORA_ERR_UNSUPPORTED;
+    GemmKParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = a->a_w; p.H = a->a_h; p.Bn = a->a_b;
+    p.bw = pow2_floor(p.W < 128 ? p.W : 128);
+    p.bh = pow2_floor(p.H < 128 / p.bw ? p.H : 128 / p.bw);
+    p.nb = 128 / (p.bw * p.bh);
+    p.tiles_w = (p.W + p.bw - 1) / p.bw;
+    p.tiles_h = (p.H + p.bh - 1) / p.bh;
+    p.tiles_b = (p.Bn + p.nb - 1) / p.nb;
+    p.N = a->n;
+    p.taps = a->kh * a->kw; p.kw = a->kw; p.pad = a->pad;
+    p.kchunks = (a->a_c + GEMM_BK - 1) / GEMM_BK;
+    p.kchunks2 = a->a2 ? (a->a2_c + GEMM_BK - 1) / GEMM_BK : 0;
+    p.geglu = a->geglu;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) return CTRLORA_ERR_CUDA;
+    }
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    // ---- pick the N tile: fewest "waves x tile-cost" over the SMs; cost of one tile ~ BN (+ fixed overhead)
+    int bn_out = a->block_n;
+    if (bn_out <= 0) {
+        long best_cost = -1;
+        const int max_out = p.geglu ? 128 : 256;
+        for (int cand = max_out; cand >= 16; cand -= 16) {
+            if (a->seg_width > 0 && a->seg_width % cand != 0) continue;
+            const int nt = (p.N + cand - 1) / cand;
+            const long tiles = (long)m_tiles * nt;
+            const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+            const long cost = waves * ((p.geglu ? 2 * cand : cand) + 24);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn_out = cand; }
+        }
+    }
+    if (bn_out % 16 != 0 || bn_out < 16 || bn_out > (p.geglu ? 128 : 256)) return CTRLORA_ERR_ARG;
+    if (a->seg_width > 0 && a->seg_width % bn_out != 0) return CTRLORA_ERR_ARG;
+    p.BN = p.geglu ? 2 * bn_out : bn_out;
+    p.n_tiles = (p.N + bn_out - 1) / bn_out;
+    p.idesc = umma_idesc_f16(GEMM_BM, p.BN, 0);
+    for (int i = 0; i < 3; ++i) { p.out[i] = a->out[i]; p.transposed[i] = a->transposed[i]; }
+    p.seg_width = a->seg_width;
+    p.ldc = a->ldc; p.out_f32 = a->out_f32;
+    p.bias = a->bias; p.rowbias = a->rowbias;
+    p.rows_per_img = a->rows_per_img > 0 ? a->rows_per_img : p.W * p.H;
+    p.residual = reinterpret_cast<const __half*>(a->residual); p.ldr = a->ldr;
+    p.out_scale = a->out_scale;
+    p.head_dim = a->head_dim; p.tok_pad = a->tok_pad;
+
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    {
+        uint64_t dims[4] = {(uint64_t)a->a_c, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
+        uint64_t str[3] = {(uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * p.W, (uint64_t)a->a_ld * 2 * p.W * p.H};
+        uint32_t box[4] = {GEMM_BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.nb};
+        int rc = make_tmap_f16(&tmA, a->a, 4, dims, str, box);
+        if (rc) return rc;
+        const uint64_t rows = p.geglu ? 2ull * p.N : (uint64_t)p.N;
+        uint64_t wd[3] = {(uint64_t)a->a_c, (uint64_t)p.taps, rows};
+        uint64_t ws[2] = {(uint64_t)a->a_c * 2, (uint64_t)a->a_c * 2 * p.taps};
+        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)bn_out};
+        rc = make_tmap_f16(&tmB, a->w, 3, wd, ws, wb);
+        if (rc) return rc;
+    }
+    if (a->a2) {
+        if (!a->w2 || a->a2_c % 8 != 0 || a->a2_ld % 8 != 0 || p.geglu) return CTRLORA_ERR_ARG;
+        uint64_t dims[4] = {(uint64_t)a->a2_c, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
+        uint64_t str[3] = {(uint64_t)a->a2_ld * 2, (uint64_t)a->a2_ld * 2 * p.W, (uint64_t)a->a2_ld * 2 * p.W * p.H};
+        uint32_t box[4] = {GEMM_BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.nb};
+        int rc = make_tmap_f16(&tmA2, a->a2, 4, dims, str, box);
+        if (rc) return rc;
+        uint64_t wd[3] = {(uint64_t)a->a2_c, 1, (uint64_t)p.N};
+        uint64_t ws[2] = {(uint64_t)a->a2_c * 2, (uint64_t)a->a2_c * 2};
+        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)bn_out};
+        rc = make_tmap_f16(&tmB2, a->w2, 3, wd, ws, wb);
+        if (rc) return rc;
+    } else {
+        tmA2 = tmA;
+        tmB2 = tmB;
+    }
+    if (!g_attr_set) {
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) !=
+            cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        g_attr_set = true;
+    }
+    const int total = m_tiles * p.n_tiles;
+    const int grid = total < g_num_sms ? total : g_num_sms;
+    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}

@@ -1,0 +1,45 @@
+// Kernel-side parameter block of the tcgen05 implicit-GEMM kernel (see gemm_sm100.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ctrl {
+
+constexpr int GEMM_BM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int GEMM_BK = 64;        // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KiB
+constexpr int GEMM_B_BYTES_MAX = 256 * GEMM_BK * 2;          // 32 KiB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES_MAX;
+constexpr int GEMM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmKParams {
+    // tile geometry over the (B, H, W) pixel grid; a plain [M, K] matrix is B=1, H=1, W=M
+    int W, H, Bn;
+    int bw, bh, nb;                 // TMA box of one 128-row tile: nb * bh * bw == 128
+    int tiles_w, tiles_h, tiles_b;  // ceil-div of the dims above by the box
+    int N;                          // output columns
+    int BN;                         // UMMA N of one tile (GEGLU: value half + gate half)
+    int n_tiles;
+    int taps, kw, pad;              // filter taps (1 or 9), filter width, zero padding
+    int kchunks;                    // ceil(Cin / 64) per tap
+    int kchunks2;                   // extra 1x1 segment from the second operand pair (0 = none)
+    int geglu;                      // 1: weights are [2N, K]; out = value * gelu(gate)
+    uint32_t idesc;
+    // epilogue
+    void* out[3];
+    int seg_width;                  // 0: single output; else column n goes to out[n / seg_width]
+    int transposed[3];              // store segment as [img, head, d, tok_pad] (V^T for attention)
+    int ldc;
+    int out_f32;
+    const float* bias;              // [N] (GEGLU: [2N])
+    const float* rowbias;           // [images, N]  per-image additive term (time embedding)
+    int rows_per_img;
+    const __half* residual;         // [M, ldr]
+    int ldr;
+    float out_scale;
+    int head_dim, tok_pad;
+    int bf16;
+};
+
+}  // namespace ctrl
