@@ -20,9 +20,20 @@ class GemmArgs(C.Structure):
         ("n", c_int), ("block_n", c_int), ("geglu", c_int),
         ("out", c_void_p * 3), ("seg_width", c_int), ("transposed", c_int * 3),
         ("ldc", c_int), ("out_f32", c_int),
-        ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int),
-        ("residual", c_void_p), ("ldr", c_int), ("out_scale", c_float),
+        ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int), ("rowbias_ld", c_int),
+        ("residual", c_void_p), ("ldr", c_int), ("residual_f32", c_int), ("out_scale", c_float),
         ("head_dim", c_int), ("tok_pad", c_int), ("bf16", c_int),
+    ]
+
+
+class GroupNormArgs(C.Structure):
+    """Mirror of `struct ctrlora_groupnorm_args`."""
+    _fields_ = [
+        ("x1", c_void_p), ("add1", c_void_p), ("add1_scale", c_float), ("c1", c_int), ("ld1", c_ll),
+        ("x2", c_void_p), ("add2", c_void_p), ("add2_scale", c_float), ("c2", c_int), ("ld2", c_ll),
+        ("batch", c_int), ("hw", c_int), ("groups", c_int),
+        ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("silu", c_int),
+        ("y", c_void_p), ("raw_out", c_void_p), ("stats_ws", c_void_p),
     ]
 
 
@@ -50,6 +61,24 @@ def load():
     return _lib
 
 
+_P, _I, _L, _F = c_void_p, c_int, c_ll, c_float
+_ARGTYPES = {
+    "ctrlora_gemm_f16": [_P, _P],
+    "ctrlora_gemm_f16_simt": [_P, _P],
+    "ctrlora_groupnorm_f16": [_P, _P],
+    "ctrlora_layernorm_f16": [_P, _L, _P, _L, _I, _I, _P, _P, _F, _P],
+    "ctrlora_attention_f16": [_P, _L, _P, _L, _P, _I, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ctrlora_nchw_f32_to_nhwc_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "ctrlora_nhwc_to_nchw_f32": [_P, _I, _L, _P, _I, _I, _I, _P],
+    "ctrlora_timestep_embedding": [_P, _P, _P, _I, _I, _P],
+    "ctrlora_small_linear": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ctrlora_upsample2x_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "ctrlora_im2col_s2_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "ctrlora_cast_transpose_f32_to_f16": [_P, _P, _L, _I, _I, _P],
+    "ctrlora_ddim_update": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P],
+}
+
+
 def _declare(lib):
     lib.ctrlora_abi_version.restype = c_int
     lib.ctrlora_last_cuda_error.restype = C.c_char_p
@@ -57,6 +86,7 @@ def _declare(lib):
         fn = getattr(lib, name)
         if name not in ("ctrlora_abi_version", "ctrlora_last_cuda_error"):
             fn.restype = c_int
+            fn.argtypes = _ARGTYPES[name]
 
 
 def check(status, what):
@@ -71,4 +101,15 @@ EXPORTS = [
     "ctrlora_last_cuda_error",
     "ctrlora_gemm_f16",
     "ctrlora_gemm_f16_simt",
+    "ctrlora_groupnorm_f16",
+    "ctrlora_layernorm_f16",
+    "ctrlora_attention_f16",
+    "ctrlora_nchw_f32_to_nhwc_f16",
+    "ctrlora_nhwc_to_nchw_f32",
+    "ctrlora_timestep_embedding",
+    "ctrlora_small_linear",
+    "ctrlora_upsample2x_f16",
+    "ctrlora_im2col_s2_f16",
+    "ctrlora_cast_transpose_f32_to_f16",
+    "ctrlora_ddim_update",
 ]

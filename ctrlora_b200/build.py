@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(ROOT, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v", "-I", CSRC, "-I", INCLUDE,
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", CSRC, "-I", INCLUDE,
 ]
 
 

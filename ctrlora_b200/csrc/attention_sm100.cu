@@ -1,0 +1,342 @@
+// Fused attention forward on tcgen05 for sm_100a:  O = softmax(Q K^T * d^-1/2) V  per (image, head, 128-query tile).
+// reference: CrossAttention.forward, ldm/modules/attention.py:163-194 (fp32 logits and softmax, scale d_head^-0.5);
+// the [8B, N, N] fp32 `sim` matrix the reference materialises (512 MiB per image at N = 4096) never exists here.
+//
+//   S = Q K^T      tcgen05.mma, operands staged by TMA (Q [128 x d], K [BKV x d], K-major, SWIZZLE_128B), S in TMEM
+//   softmax        128 threads, one query row each (TMEM lane == thread): no cross-thread reductions at all;
+//                  fp32 max / exp2 / sum, P written to shared memory as fp16 in the UMMA K-major swizzled layout
+//   PV = P V       tcgen05.mma with A = P (smem), B = V^T tile ([d x BKV], K-major; the V projection GEMM stores V
+//                  transposed for exactly this), result in TMEM
+// MULTI (long key sequences, d <= 80): online softmax, running output kept in registers, rescaled per KV tile.
+// single-tile (Nk <= BKV, any d <= 160): exact two-pass softmax, P aliases the dead K buffer.
+#include "common.cuh"
+#include "ctrlora_b200.h"
+#include "gemm_sm100.cuh"
+#include <string.h>
+
+namespace ctrl {
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+struct AttnParams {
+    int Nq, Nk, heads, d, d16;  // d16 = d rounded up to 16 (UMMA N of the PV product)
+    int nkc;                    // K-chunks of 64 over d
+    int n_kv_tiles;
+    float scale_log2e;          // d^-1/2 * log2(e)
+    __half* out;
+    long long ldo;
+    uint32_t idesc_s, idesc_pv;
+};
+
+constexpr int ATT_THREADS = 192;  // warps 0-3: softmax / epilogue (TMEM lane groups 0-3), warp 4: TMA, warp 5: MMA
+
+template <int DPAD, int BKV, bool MULTI>
+struct AttnSmem {
+    static constexpr int NKC = (DPAD + 63) / 64;
+    static constexpr int Q_BYTES = NKC * 128 * 128;
+    static constexpr int K_BYTES = NKC * BKV * 128;
+    static constexpr int V_CHUNK = DPAD * 128;
+    static constexpr int V_BYTES = (BKV / 64) * V_CHUNK;
+    static constexpr int P_BYTES = (BKV / 64) * 128 * 128;
+    static constexpr int STAGES = MULTI ? 2 : 1;
+    static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+    static constexpr int P_OFF = MULTI ? (Q_BYTES + STAGES * STAGE_BYTES) : Q_BYTES;  // single tile: P aliases K
+    static constexpr int DATA_BYTES = MULTI ? (P_OFF + P_BYTES)
+                                            : (Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES) + V_BYTES);
+    static constexpr int V_OFF_SINGLE = Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES);
+    static constexpr int TOTAL = DATA_BYTES + 1024 + 128;
+    static constexpr int TMEM_COLS = (BKV + DPAD) <= 256 ? 256 : 512;
+};
+
+template <int DPAD, int BKV, bool MULTI>
+__global__ void __launch_bounds__(ATT_THREADS, (MULTI && DPAD <= 48) ? 2 : 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+    using L = AttnSmem<DPAD, BKV, MULTI>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;   // [2]
+    uint64_t* kv_empty = bars + 3;  // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* pv_full = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+
+    uint8_t* sQ = smem;
+    auto sK = [&](int stage) { return smem + L::Q_BYTES + (MULTI ? stage * L::STAGE_BYTES : 0); };
+    auto sV = [&](int stage) { return MULTI ? smem + L::Q_BYTES + stage * L::STAGE_BYTES + L::K_BYTES : smem + L::V_OFF_SINGLE; };
+    uint8_t* sP = smem + L::P_OFF;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 5 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(pv_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_s = tmem_base;          // [0, BKV)
+    const uint32_t tmem_pv = tmem_base + BKV;   // [BKV, BKV + d16)
+    const int n_tiles = p.n_kv_tiles;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            mbar_expect_tx(q_full, p.nkc * 128 * 128);
+            for (int kc = 0; kc < p.nkc; ++kc) tma_load_4d(sQ + kc * 128 * 128, &tmQ, q_full, kc * 64, head, q0, img);
+            const uint32_t tx = p.nkc * BKV * 128 + (BKV / 64) * p.d16 * 128;
+            for (int j = 0; j < n_tiles; ++j) {
+                const int stage = MULTI ? (j & 1) : 0;
+                if (MULTI && j >= 2) mbar_wait(&kv_empty[stage], ((j >> 1) - 1) & 1);
+                mbar_expect_tx(&kv_full[stage], tx);
+                for (int kc = 0; kc < p.nkc; ++kc)
+                    tma_load_4d(sK(stage) + kc * BKV * 128, &tmK, &kv_full[stage], kc * 64, head, j * BKV, img);
+                for (int c = 0; c < BKV / 64; ++c)
+                    tma_load_4d(sV(stage) + c * L::V_CHUNK, &tmV, &kv_full[stage], j * BKV + c * 64, 0, head, img);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            const int ksteps_s = (p.d + 15) / 16;
+            auto issue_s = [&](int stage) {
+                const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK(stage));
+                for (int ks = 0; ks < ksteps_s; ++ks) {
+                    const uint32_t off_q = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    const uint32_t off_k = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
+                    umma_f16(tmem_s, umma_desc_kmajor_sw128(qa + off_q), umma_desc_kmajor_sw128(ka + off_k), p.idesc_s,
+                             ks != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int stage = MULTI ? (j & 1) : 0;
+                mbar_wait(p_full, j & 1);  // P[j] in smem, S[j] read out, PV[j-1] read out
+                tc_fence_after();
+                const uint32_t pa = smem_u32(sP), va = smem_u32(sV(stage));
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    const uint32_t off_v = (ks >> 2) * L::V_CHUNK + (ks & 3) * 32;
+                    umma_f16(tmem_pv, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
+                             ks != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_full);
+                if (MULTI) umma_commit(&kv_empty[stage]);
+                if (j + 1 < n_tiles) {
+                    const int ns = (j + 1) & 1;
+                    mbar_wait(&kv_full[ns], ((j + 1) >> 1) & 1);
+                    tc_fence_after();
+                    issue_s(ns);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------- softmax + epilogue: thread == query row
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o_reg[MULTI ? DPAD : 1];
+        if (MULTI) {
+#pragma unroll
+            for (int i = 0; i < DPAD; ++i) o_reg[i] = 0.f;
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv_valid = min(BKV, p.Nk - j * BKV);  // columns >= kv_valid are TMA zero fill: masked out
+            // pass 1: row max
+            float m_tile = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_s + lane_off + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(raw[i]));
+            }
+            const float m_new = fmaxf(m_run, m_tile);
+            const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // first tile: exp2(-inf) = 0
+            m_run = m_new;
+            const float neg_ms = -m_new * p.scale_log2e;
+            if (MULTI && j > 0) {
+                // fold the previous tile's PV (relative to the previous max), then rescale to the new max
+                mbar_wait(pv_full, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < DPAD; c += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x16(tmem_pv + lane_off + c, raw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o_reg[c + i] = (o_reg[c + i] + __uint_as_float(raw[i])) * alpha;
+                }
+            }
+            // pass 2: P = exp2(s * scale*log2e - m * scale*log2e) -> fp16, swizzled K-major rows of 128 B
+            float l_tile = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_s + lane_off + c, raw);
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2e, neg_ms)) : 0.f;
+                    float p1 = (c + i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2e, neg_ms)) : 0.f;
+                    __half2 h = __floats2half2_rn(p0, p1);
+                    // the row sum uses the fp16-rounded probabilities the PV product will actually see
+                    float2 f = __half22float2(h);
+                    l_tile += f.x + f.y;
+                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                uint8_t* chunk = sP + (c >> 6) * 128 * 128 + r * 128;
+                const int u0 = (c & 63) >> 3;  // first 16-byte unit of this 32-column group within the 128 B row
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 val = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+                    *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = val;
+                }
+            }
+            l_run = l_run * alpha + l_tile;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- final: fold the last PV, normalise, store
+        mbar_wait(pv_full, (n_tiles - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        const bool row_ok = (q0 + r) < p.Nq;
+        __half* orow = p.out + (static_cast<long long>(img) * p.Nq + q0 + r) * p.ldo + head * p.d;
+#pragma unroll
+        for (int c = 0; c < DPAD; c += 16) {
+            if (c < p.d) {  // warp-uniform
+                uint32_t raw[16];
+                tmem_ld_32x16(tmem_pv + lane_off + c, raw);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float acc = __uint_as_float(raw[i]);
+                    if (MULTI) acc += o_reg[c + i];
+                    v[i] = acc * inv_l;
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (c + g * 8 < p.d) {
+                            uint4 u;
+                            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                            *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+template <int DPAD, int BKV, bool MULTI>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                       cudaStream_t stream) {
+    using L = AttnSmem<DPAD, BKV, MULTI>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attention_kernel<DPAD, BKV, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 L::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    attention_kernel<DPAD, BKV, MULTI><<<grid, ATT_THREADS, L::TOTAL, stream>>>(tq, tk, tv, p);
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+}  // namespace ctrl
+
+using namespace ctrl;
+
+extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt,
+                                     int nk_pad, void* out, long long ldo, int batch, int heads, int nq, int nk,
+                                     int head_dim, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!q || !k || !vt || !out) return CTRLORA_ERR_ARG;
+    const int d = head_dim;
+    if (d % 8 != 0 || d > 160 || nk_pad % 8 != 0 || nk_pad < nk || ldq % 8 != 0 || ldk % 8 != 0 || ldo % 8 != 0)
+        return CTRLORA_ERR_ARG;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.Nq = nq; p.Nk = nk; p.heads = heads; p.d = d; p.d16 = (d + 15) / 16 * 16; p.nkc = (d + 63) / 64;
+    p.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
+    p.out = reinterpret_cast<__half*>(out); p.ldo = ldo;
+    const bool multi = nk > 256;
+    if (multi && d > 80) return CTRLORA_ERR_UNSUPPORTED;  // d_head 160 with > 256 keys: not on the 512x512 path
+    const int bkv = multi ? 128 : (nk <= 128 ? 128 : 256);
+    p.n_kv_tiles = (nk + bkv - 1) / bkv;
+    p.idesc_s = umma_idesc_f16(128, bkv, 0);
+    p.idesc_pv = umma_idesc_f16(128, p.d16, 0);
+    CUtensorMap tq, tk, tv;
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)nq, (uint64_t)batch};
+        uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)ldq * 2 * nq};
+        uint32_t box[4] = {64, 1, 128, 1};
+        int rc = make_tmap_f16(&tq, q, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)nk, (uint64_t)batch};
+        uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldk * 2, (uint64_t)ldk * 2 * nk};
+        uint32_t box[4] = {64, 1, (uint32_t)bkv, 1};
+        int rc = make_tmap_f16(&tk, k, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)nk, (uint64_t)d, (uint64_t)heads, (uint64_t)batch};
+        uint64_t str[3] = {(uint64_t)nk_pad * 2, (uint64_t)nk_pad * 2 * d, (uint64_t)nk_pad * 2 * d * heads};
+        uint32_t box[4] = {64, (uint32_t)p.d16, 1, 1};
+        int rc = make_tmap_f16(&tv, vt, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    dim3 grid((nq + 127) / 128, heads, batch);
+    if (multi) {
+        if (d <= 48) return launch_attn<48, 128, true>(tq, tk, tv, p, grid, stream);
+        return launch_attn<80, 128, true>(tq, tk, tv, p, grid, stream);
+    }
+    if (bkv == 128) {
+        if (d <= 48) return launch_attn<48, 128, false>(tq, tk, tv, p, grid, stream);
+        if (d <= 80) return launch_attn<80, 128, false>(tq, tk, tv, p, grid, stream);
+        return launch_attn<160, 128, false>(tq, tk, tv, p, grid, stream);
+    }
+    if (d <= 48) return launch_attn<48, 256, false>(tq, tk, tv, p, grid, stream);
+    if (d <= 80) return launch_attn<80, 256, false>(tq, tk, tv, p, grid, stream);
+    return launch_attn<160, 256, false>(tq, tk, tv, p, grid, stream);
+}

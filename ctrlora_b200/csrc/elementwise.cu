@@ -1,0 +1,260 @@
+// Small HBM/latency-bound kernels of the hot path: layout/dtype conversion at the module boundary, timestep embedding,
+// the M = batch linears of the time-embedding MLP, nearest-2x upsample, the stride-2 gather, weight preparation and
+// the DDIM update.
+#include "common.cuh"
+#include "ctrlora_b200.h"
+
+namespace ctrl {
+
+// ---- NCHW fp32 (reference tensor layout) -> pixel-major fp16 with the channel dim zero-padded to c_pad
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, __half* __restrict__ dst, int B, int C, int HW, int c_pad) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * HW * c_pad;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % c_pad);
+    const long long pix = i / c_pad;
+    const int b = static_cast<int>(pix / HW), p = static_cast<int>(pix % HW);
+    dst[i] = c < C ? __float2half_rn(src[(static_cast<long long>(b) * C + c) * HW + p]) : __float2half_rn(0.f);
+}
+
+// ---- pixel-major (fp16 or fp32, row stride ld) -> NCHW fp32, first C channels
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, long long ld, float* __restrict__ dst, int B, int C, int HW) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * C * HW;
+    if (i >= total) return;
+    const int p = static_cast<int>(i % HW);
+    const int c = static_cast<int>((i / HW) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+    dst[i] = static_cast<float>(src[(static_cast<long long>(b) * HW + p) * ld + c]);
+}
+
+// ---- timestep_embedding: out[b] = [cos(t*f) | sin(t*f)], freqs computed on the host exactly like the reference
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, const float* __restrict__ freqs,
+                                          float* __restrict__ out, int B, int half) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, k = i % half;
+    const float arg = __fmul_rn(static_cast<float>(t[b]), freqs[k]);
+    out[b * 2 * half + k] = cosf(arg);
+    out[b * 2 * half + half + k] = sinf(arg);
+}
+
+// ---- y[b, n] = act_out( sum_k act_in(x[b, k]) * W[n, k] + bias[n] ),  b < rows <= 8 per pass; one warp per n.
+// fp32 activations (the time embedding stays fp32 end to end), fp16 weights.
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ y, int ldy, int rows, int N, int K, int silu_in, int silu_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+        for (int k = lane * 8; k < K; k += 256) {
+            uint4 u = *reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+            float wv[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); wv[2 * e] = f.x; wv[2 * e + 1] = f.y; }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (r0 + r < rows) {
+                    const float* xp = x + static_cast<long long>(r0 + r) * ldx + k;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float xv = xp[e];
+                        if (silu_in) xv = silu_f(xv);
+                        acc[r] += xv * wv[e];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (r0 + r < rows) {
+                    float v = acc[r] + (bias ? bias[n] : 0.f);
+                    if (silu_out) v = silu_f(v);
+                    y[static_cast<long long>(r0 + r) * ldy + n] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---- nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, mode='nearest')), pixel-major fp16, 16 B vectors
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int vecs) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * 4 * H * W * vecs;
+    if (i >= total) return;
+    const int v = static_cast<int>(i % vecs);
+    long long pix = i / vecs;
+    const int ow = static_cast<int>(pix % (2 * W));
+    pix /= 2 * W;
+    const int oh = static_cast<int>(pix % (2 * H));
+    const int b = static_cast<int>(pix / (2 * H));
+    dst[i] = src[((static_cast<long long>(b) * H + (oh >> 1)) * W + (ow >> 1)) * vecs + v];
+}
+
+// ---- stride-2 3x3 pad-1 gather: col[b, oh, ow, tap, c] = x[b, 2*oh + kh - 1, 2*ow + kw - 1, c] (0 outside)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int vecs) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * Ho * Wo * 9 * vecs;
+    if (i >= total) return;
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int tap = static_cast<int>(r % 9);
+    r /= 9;
+    const int ow = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int oh = static_cast<int>(r % Ho);
+    const int b = static_cast<int>(r / Ho);
+    const int ih = 2 * oh + tap / 3 - 1, iw = 2 * ow + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = src[((static_cast<long long>(b) * H + ih) * W + iw) * vecs + v];
+    dst[i] = val;
+}
+
+// ---- weight preparation: fp32 [batch, R, C] -> fp16 [batch, C, R]  (Conv2d [Cout, Cin, 3*3] -> [Cout, 9, Cin];
+// R == 1 is a plain cast), optional zero padding of C_out dim handled by the caller's buffer.
+__global__ void cast_transpose_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long batch, int R, int C) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = batch * R * C;
+    if (i >= total) return;
+    const int r = static_cast<int>(i % R);  // dst index: [b][c][r]
+    const int c = static_cast<int>((i / R) % C);
+    const long long b = i / (static_cast<long long>(R) * C);
+    dst[i] = __float2half_rn(src[(b * R + r) * C + c]);
+}
+
+// ---- DDIM update, one pass: CFG combine + pred_x0 + x_prev; explicit round-to-nearest ops in the reference's
+// order (cldm/ddim_hacked.py:192,215,226-230) so that no FMA contraction changes the fp32 results.
+// stats[b] += sum(x_prev^2) of image b (warp-reduced), a per-step scalar the host can read back.
+__global__ void __launch_bounds__(256)
+ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_cond, const float* __restrict__ e_uncond,
+                   const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                   float* __restrict__ stats, int per_image, int total, float cfg_scale, float sqrt_a_t,
+                   float sqrt_a_prev, float dir_coef, float sigma_t, float temperature, float sqrt_one_minus_at) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f;
+    int img = 0;
+    if (i < total) {
+        float e = e_cond[i];
+        if (e_uncond) {
+            const float u = e_uncond[i];
+            e = __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(e, u)));
+        }
+        const float p0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sqrt_one_minus_at, e)), sqrt_a_t);
+        const float dir = __fmul_rn(dir_coef, e);
+        float xp = __fadd_rn(__fmul_rn(sqrt_a_prev, p0), dir);
+        xp = __fadd_rn(xp, noise ? __fmul_rn(__fmul_rn(sigma_t, noise[i]), temperature) : 0.f);
+        x_prev[i] = xp;
+        pred_x0[i] = p0;
+        sq = xp * xp;
+        img = i / per_image;
+    }
+    if (stats) {
+        // per_image is a multiple of 32 for every latent shape on this path, so a warp never straddles two images
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if ((threadIdx.x & 31) == 0 && i < total) atomicAdd(&stats[img], sq);
+    }
+}
+
+static inline unsigned blocks_for(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace ctrl
+
+using namespace ctrl;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA)
+
+extern "C" int ctrlora_nchw_f32_to_nhwc_f16(const float* src, void* dst, int batch, int channels, int hw, int c_pad,
+                                            void* stream) {
+    if (!src || !dst || c_pad < channels) return CTRLORA_ERR_ARG;
+    const long long total = static_cast<long long>(batch) * hw * c_pad;
+    nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__half*>(dst), batch,
+                                                                           channels, hw, c_pad);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_nhwc_to_nchw_f32(const void* src, int src_is_f32, long long ld, float* dst, int batch,
+                                        int channels, int hw, void* stream) {
+    if (!src || !dst) return CTRLORA_ERR_ARG;
+    const long long total = static_cast<long long>(batch) * channels * hw;
+    if (src_is_f32)
+        nhwc_to_nchw_kernel<float><<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(
+            reinterpret_cast<const float*>(src), ld, dst, batch, channels, hw);
+    else
+        nhwc_to_nchw_kernel<__half><<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(
+            reinterpret_cast<const __half*>(src), ld, dst, batch, channels, hw);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_timestep_embedding(const long long* t, const float* freqs, float* out, int batch, int half,
+                                          void* stream) {
+    if (!t || !freqs || !out) return CTRLORA_ERR_ARG;
+    timestep_embedding_kernel<<<blocks_for(static_cast<long long>(batch) * half, 128), 128, 0, STREAM(stream)>>>(
+        t, freqs, out, batch, half);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_small_linear(const float* x, int ldx, const void* w, const float* bias, float* y, int ldy,
+                                    int rows, int n, int k, int silu_in, int silu_out, void* stream) {
+    if (!x || !w || !y || k % 8 != 0 || ldx % 4 != 0) return CTRLORA_ERR_ARG;
+    small_linear_kernel<<<(n + 7) / 8, 256, 0, STREAM(stream)>>>(x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy,
+                                                                 rows, n, k, silu_in, silu_out);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_upsample2x_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream) {
+    if (!src || !dst || channels % 8 != 0) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    const long long total = static_cast<long long>(batch) * 4 * h * w * vecs;
+    upsample2x_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(src),
+                                                                        reinterpret_cast<uint4*>(dst), batch, h, w, vecs);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_im2col_s2_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream) {
+    if (!src || !dst || channels % 8 != 0 || (h & 1) || (w & 1)) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * vecs;
+    im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(src),
+                                                                       reinterpret_cast<uint4*>(dst), batch, h, w, vecs);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, long long batch, int rows, int cols,
+                                                 void* stream) {
+    if (!src || !dst) return CTRLORA_ERR_ARG;
+    const long long total = batch * rows * cols;
+    cast_transpose_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__half*>(dst), batch,
+                                                                            rows, cols);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise,
+                                   float* x_prev, float* pred_x0, float* stats, int batch, int per_image,
+                                   float cfg_scale, float a_t, float a_prev, float sigma_t, float sqrt_one_minus_at,
+                                   float temperature, void* stream) {
+    if (!x || !e_cond || !x_prev || !pred_x0 || (stats && per_image % 32 != 0)) return CTRLORA_ERR_ARG;
+    // per-step scalars exactly as the reference forms them from fp32 tensors (cldm/ddim_hacked.py:208-227):
+    // a_t.sqrt(), a_prev.sqrt(), (1 - a_prev - sigma_t**2).sqrt(), sigma_t * temperature
+    const float sqrt_a_t = sqrtf(a_t), sqrt_a_prev = sqrtf(a_prev);
+    const float dir_coef = sqrtf((1.0f - a_prev) - sigma_t * sigma_t);
+    const int total = batch * per_image;
+    if (stats && cudaMemsetAsync(stats, 0, sizeof(float) * batch, STREAM(stream)) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    ddim_update_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(
+        x, e_cond, e_uncond, noise, x_prev, pred_x0, stats, per_image, total, cfg_scale, sqrt_a_t, sqrt_a_prev, dir_coef,
+        sigma_t, temperature, sqrt_one_minus_at);
+    return LAUNCH_OK();
+}

@@ -171,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 if (row_ok) {
                     if (p.rowbias) {
-                        const float* rb = p.rowbias + static_cast<long long>(img) * p.N + nbase;
+                        const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + nbase;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (nbase + j < p.N) v[j] += __ldg(rb + j);
@@ -181,7 +181,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
                     }
                     const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
-                    if (p.residual) {
+                    if (p.residual && p.residual_f32) {
+                        const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
+                        for (int j = 0; j < 32; ++j)
+                            if (c + j < bn_out && nbase + j < p.N) v[j] += rp[j];
+                    } else if (p.residual) {
                         const __half* rp = p.residual + m * p.ldr + nbase;
                         if (full_chunk && (p.ldr & 7) == 0) {
 #pragma unroll
@@ -358,6 +362,8 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     p.bias = a->bias; p.rowbias = a->rowbias;
     p.rows_per_img = a->rows_per_img > 0 ? a->rows_per_img : p.W * p.H;
     p.residual = reinterpret_cast<const __half*>(a->residual); p.ldr = a->ldr;
+    p.residual_f32 = a->residual_f32;
+    p.rowbias_ld = a->rowbias_ld > 0 ? a->rowbias_ld : a->n;
     p.out_scale = a->out_scale;
     p.head_dim = a->head_dim; p.tok_pad = a->tok_pad;
 

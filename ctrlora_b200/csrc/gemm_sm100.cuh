@@ -35,6 +35,8 @@ struct GemmKParams {
     const float* bias;              // [N] (GEGLU: [2N])
     const float* rowbias;           // [images, N]  per-image additive term (time embedding)
     int rows_per_img;
+    int rowbias_ld;
+    int residual_f32;
     const __half* residual;         // [M, ldr]
     int ldr;
     float out_scale;

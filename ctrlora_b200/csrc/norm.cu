@@ -1,0 +1,222 @@
+// GroupNorm(+SiLU) and LayerNorm for pixel-major fp16 activations (HBM-bound kernels; fp32 statistics).
+//   GroupNorm32 -> SiLU before every ResBlock conv    reference: ldm/modules/diffusionmodules/openaimodel.py:190-197,
+//                                                     221-231 with GroupNorm32 = fp32 statistics, util.py:202-219
+//   GroupNorm(eps 1e-6) at the SpatialTransformer     reference: ldm/modules/attention.py:88-89,327
+//   LayerNorm(eps 1e-5)                               reference: ldm/modules/attention.py:263-265,272-274
+// The GroupNorm input may be the channel concatenation [x1 (+ s1*add1) | x2 (+ s2*add2)]: that is the UNet decoder's
+// `cat([h, hs.pop() + control.pop()], 1)` (cldm/cldm.py:34-42) read in place — the concat and the ControlNet residual
+// adds never make a round trip through HBM on their own.
+#include "common.cuh"
+#include "ctrlora_b200.h"
+
+namespace ctrl {
+
+struct GnSrc {
+    const __half* x1; const __half* add1; float s1; int c1; long long ld1;
+    const __half* x2; const __half* add2; float s2; int c2; long long ld2;
+};
+
+__device__ __forceinline__ void load8(const GnSrc& s, long long pix, int c, float* v) {
+    // c is a multiple of 8; c1 is a multiple of 8, so a vector never straddles the two sources
+    const __half* x; const __half* ad; float sc; long long off;
+    if (c < s.c1) { x = s.x1; ad = s.add1; sc = s.s1; off = pix * s.ld1 + c; }
+    else { x = s.x2; ad = s.add2; sc = s.s2; off = pix * s.ld2 + (c - s.c1); }
+    uint4 u = *reinterpret_cast<const uint4*>(x + off);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    if (ad) {
+        uint4 w = *reinterpret_cast<const uint4*>(ad + off);
+        const __half2* g = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { float2 f = __half22float2(g[e]); v[2 * e] += sc * f.x; v[2 * e + 1] += sc * f.y; }
+    }
+}
+
+// stats[b][g] = {sum, sumsq} accumulated with atomics (buffer zeroed by the launcher)
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __restrict__ stats) {
+    extern __shared__ float sm[];  // [2][C]
+    float* csum = sm;
+    float* csq = sm + C;
+    const int b = blockIdx.y;
+    const int vecs = C >> 3;
+    const int lanes = blockDim.x / vecs;  // pixel lanes
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    if (pl < lanes) {
+        float a[8], q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] = 0.f; q[e] = 0.f; }
+        for (int p = p0 + pl; p < p1; p += lanes) {
+            float v[8];
+            load8(s, static_cast<long long>(b) * HW + p, vec * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] += v[e]; q[e] += v[e] * v[e]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(&csum[vec * 8 + e], a[e]); atomicAdd(&csq[vec * 8 + e], q[e]); }
+    }
+    __syncthreads();
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += csum[c]; sq += csq[c]; }
+        atomicAdd(&stats[(b * groups + g) * 2], su);
+        atomicAdd(&stats[(b * groups + g) * 2 + 1], sq);
+    }
+}
+
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const float* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                __half* __restrict__ y, __half* __restrict__ raw) {
+    const int b = blockIdx.y;
+    const int vecs = C >> 3;
+    const int lanes = blockDim.x / vecs;
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    if (pl >= lanes) return;
+    const int cpg = C / groups;
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * HW);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = vec * 8 + e;
+        const int g = c / cpg;
+        const float mean = stats[(b * groups + g) * 2] * inv_n;
+        const float var = fmaxf(stats[(b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        sc[e] = rstd * gamma[c];
+        sh[e] = beta[c] - mean * sc[e];
+    }
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    for (int p = p0 + pl; p < p1; p += lanes) {
+        const long long pix = static_cast<long long>(b) * HW + p;
+        float v[8];
+        load8(s, pix, vec * 8, v);
+        if (raw) {
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(raw + pix * C + vec * 8) = u;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float t = v[e] * sc[e] + sh[e];
+            v[e] = silu ? silu_f(t) : t;
+        }
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        *reinterpret_cast<uint4*>(y + pix * C + vec * 8) = u;
+    }
+}
+
+// one warp per row; the row stays in registers between the mean and variance passes (C <= 2048)
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, int M, int C,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int vecs = C >> 3;
+    float v[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs) {
+            uint4 u = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += v[i][e];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < vecs) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs) {
+            float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+            float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8), b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 u;
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                h[e] = __floats2half2_rn((v[i][2 * e] - mean) * rstd * g[2 * e] + bb[2 * e],
+                                         (v[i][2 * e + 1] - mean) * rstd * g[2 * e + 1] + bb[2 * e + 1]);
+            *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = u;
+        }
+    }
+}
+
+}  // namespace ctrl
+
+using namespace ctrl;
+
+extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->x1 || !a->y || !a->stats_ws || !a->gamma || !a->beta) return CTRLORA_ERR_ARG;
+    const int C = a->c1 + (a->x2 ? a->c2 : 0);
+    if (C % 8 != 0 || a->c1 % 8 != 0 || C % a->groups != 0 || C / 8 > 512) return CTRLORA_ERR_ARG;
+    if (a->ld1 % 8 != 0 || (a->x2 && a->ld2 % 8 != 0)) return CTRLORA_ERR_ARG;
+    GnSrc s;
+    s.x1 = reinterpret_cast<const __half*>(a->x1); s.add1 = reinterpret_cast<const __half*>(a->add1); s.s1 = a->add1_scale;
+    s.c1 = a->c1; s.ld1 = a->ld1;
+    s.x2 = reinterpret_cast<const __half*>(a->x2); s.add2 = reinterpret_cast<const __half*>(a->add2); s.s2 = a->add2_scale;
+    s.c2 = a->x2 ? a->c2 : 0; s.ld2 = a->ld2;
+    const int HW = a->hw, B = a->batch;
+    if (cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    // ~4 blocks per SM in total, at least 8 pixels per block
+    int chunks = (592 + B - 1) / B;
+    int ppb = (HW + chunks - 1) / chunks;
+    if (ppb < 8) ppb = 8;
+    chunks = (HW + ppb - 1) / ppb;
+    dim3 grid(chunks, B);
+    const int vecs = C / 8;
+    const int lanes = vecs >= 256 ? 1 : 256 / vecs;
+    const int threads = vecs * lanes;  // every thread owns one 8-channel vector of one pixel lane
+    gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(s, C, HW, a->groups, ppb,
+                                                                 reinterpret_cast<float*>(a->stats_ws));
+    gn_apply_kernel<<<grid, threads, 0, stream>>>(s, C, HW, a->groups, ppb, reinterpret_cast<const float*>(a->stats_ws),
+                                              a->gamma, a->beta, a->eps, a->silu, reinterpret_cast<__half*>(a->y),
+                                              reinterpret_cast<__half*>(a->raw_out));
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+extern "C" int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, int rows, int cols,
+                                     const float* gamma, const float* beta, float eps, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !y || cols % 8 != 0 || cols > 2048 || ldx % 8 != 0 || ldy % 8 != 0) return CTRLORA_ERR_ARG;
+    const int grid = (rows + 7) / 8;
+    const __half* xp = reinterpret_cast<const __half*>(x);
+    __half* yp = reinterpret_cast<__half*>(y);
+    if (cols <= 512) layernorm_kernel<2><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    else if (cols <= 1280) layernorm_kernel<5><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    else layernorm_kernel<8><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}

@@ -35,7 +35,8 @@ def _as_bhwc(a):
     return b, h, w, c, ld
 
 
-def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, residual=None, out_scale=1.0, a2=None, w2=None,
+def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0, residual=None, out_scale=1.0, a2=None,
+         w2=None,
          geglu=False, out=None, out_f32=False, seg_outs=None, seg_width=0, transposed=(0, 0, 0), head_dim=0,
          tok_pad=0, block_n=0, simt=False):
     """out = epilogue(conv_or_linear(a, w) [+ a2 @ w2^T]); see `ctrlora_gemm_f16` in include/ctrlora_b200.h.
@@ -76,13 +77,162 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, residual=Non
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == n_rows
     if rowbias is not None:
-        assert rowbias.dtype == torch.float32 and rowbias.shape[-1] == n and rowbias.is_contiguous()
-    args.bias, args.rowbias, args.rows_per_img = _ptr(bias), _ptr(rowbias), rows_per_img
+        assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
+        rowbias_ld = rowbias_ld or rowbias.stride(0)
+    args.bias, args.rowbias, args.rows_per_img, args.rowbias_ld = _ptr(bias), _ptr(rowbias), rows_per_img, rowbias_ld
     if residual is not None:
-        assert residual.dtype == torch.float16 and residual.stride(-1) == 1
+        assert residual.dtype in (torch.float16, torch.float32) and residual.stride(-1) == 1
         args.residual, args.ldr = _ptr(residual), residual.stride(-2)
+        args.residual_f32 = int(residual.dtype == torch.float32)
     args.out_scale, args.head_dim, args.tok_pad, args.bf16 = float(out_scale), head_dim, tok_pad, 0
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
-    check(fn(C.byref(args), _stream()), "ctrlora_gemm_f16")
+    check(fn(C.addressof(args), _sp()), "ctrlora_gemm_f16")
     return ret
+
+
+def _dp(t):
+    """raw device pointer (or NULL) for argtypes-declared entry points"""
+    return t.data_ptr() if t is not None else None
+
+
+def _sp():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None, add2_scale=1.0,
+              groups=32, want_raw=False, stats_ws=None):
+    """GroupNorm(+SiLU) over [x1 (+s1*add1) | x2 (+s2*add2)], pixel-major fp16 [B,H,W,C*]; returns y (and raw concat)."""
+    _require_cuda(x1, x2, add1, add2)
+    b, h, w, c1, ld1 = _as_bhwc(x1)
+    c2, ld2 = 0, 0
+    if x2 is not None:
+        b2, h2, w2, c2, ld2 = _as_bhwc(x2)
+        assert (b2, h2, w2) == (b, h, w)
+    for ad, ref in ((add1, x1), (add2, x2)):
+        if ad is not None:
+            assert ad.shape == ref.shape and ad.stride() == ref.stride() and ad.dtype == torch.float16
+    C = c1 + c2
+    y = torch.empty((b, h, w, C), device=x1.device, dtype=torch.float16)
+    raw = torch.empty_like(y) if want_raw else None
+    if stats_ws is None:
+        stats_ws = torch.empty(b * groups * 2, device=x1.device, dtype=torch.float32)
+    a = _lib.GroupNormArgs()
+    a.x1, a.add1, a.add1_scale, a.c1, a.ld1 = _dp(x1), _dp(add1), float(add1_scale), c1, ld1
+    a.x2, a.add2, a.add2_scale, a.c2, a.ld2 = _dp(x2), _dp(add2), float(add2_scale), c2, ld2
+    a.batch, a.hw, a.groups = b, h * w, groups
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == C
+    a.gamma, a.beta, a.eps, a.silu = _dp(gamma), _dp(beta), float(eps), int(silu)
+    a.y, a.raw_out, a.stats_ws = _dp(y), _dp(raw), _dp(stats_ws)
+    check(_lib.load().ctrlora_groupnorm_f16(C.addressof(a), _sp()), "ctrlora_groupnorm_f16")
+    return (y, raw) if want_raw else y
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    """x fp16 [..., C] with contiguous last dim and uniform row stride."""
+    _require_cuda(x)
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    y = torch.empty((x2.shape[0], cols), device=x.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_layernorm_f16(_dp(x2), x2.stride(0), _dp(y), cols, x2.shape[0], cols, _dp(gamma), _dp(beta),
+                                            float(eps), _sp()), "ctrlora_layernorm_f16")
+    return y.view(x.shape)
+
+
+def attention(q, k, vt, batch, heads, nq, nk, head_dim, out=None):
+    """q [batch*nq, heads*d], k [batch*nk, heads*d], vt [batch, heads, d, nk_pad] (fp16) -> [batch*nq, heads*d]."""
+    _require_cuda(q, k, vt)
+    if out is None:
+        out = torch.empty((batch * nq, heads * head_dim), device=q.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_attention_f16(_dp(q), q.stride(0), _dp(k), k.stride(0), _dp(vt), vt.shape[-1], _dp(out),
+                                            out.stride(0), batch, heads, nq, nk, head_dim, _sp()),
+          "ctrlora_attention_f16")
+    return out
+
+
+def nchw_to_nhwc_f16(x, c_pad=None):
+    """fp32 [B,C,H,W] contiguous -> fp16 [B,H,W,c_pad] (zero-padded channels)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    b, c, h, w = x.shape
+    c_pad = c_pad or c
+    y = torch.empty((b, h, w, c_pad), device=x.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_nchw_f32_to_nhwc_f16(_dp(x), _dp(y), b, c, h * w, c_pad, _sp()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw_f32(x, channels=None):
+    """[B,H,W,ld] fp16/fp32 pixel-major -> fp32 [B,channels,H,W]."""
+    _require_cuda(x)
+    b, h, w, c, ld = _as_bhwc(x)
+    channels = channels or c
+    y = torch.empty((b, channels, h, w), device=x.device, dtype=torch.float32)
+    check(_lib.load().ctrlora_nhwc_to_nchw_f32(_dp(x), int(x.dtype == torch.float32), ld, _dp(y), b, channels, h * w,
+                                               _sp()), "nhwc_to_nchw")
+    return y
+
+
+def timestep_embedding(t, freqs):
+    """t int64 [B] (device), freqs fp32 [half] (device) -> fp32 [B, 2*half]"""
+    _require_cuda(t, freqs)
+    assert t.dtype == torch.int64 and freqs.dtype == torch.float32
+    out = torch.empty((t.shape[0], 2 * freqs.shape[0]), device=t.device, dtype=torch.float32)
+    check(_lib.load().ctrlora_timestep_embedding(_dp(t), _dp(freqs), _dp(out), t.shape[0], freqs.shape[0], _sp()),
+          "timestep_embedding")
+    return out
+
+
+def small_linear(x, w, bias, silu_in=False, silu_out=False, out=None):
+    """x fp32 [rows, K] (row stride free), w fp16 [N, K] -> fp32 [rows, N]"""
+    _require_cuda(x, w)
+    assert x.dtype == torch.float32 and w.dtype == torch.float16 and w.is_contiguous() and x.stride(1) == 1
+    rows, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((rows, n), device=x.device, dtype=torch.float32)
+    check(_lib.load().ctrlora_small_linear(_dp(x), x.stride(0), _dp(w), _dp(bias), _dp(out), out.stride(0), rows, n, k,
+                                           int(silu_in), int(silu_out), _sp()), "small_linear")
+    return out
+
+
+def upsample2x(x):
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float16
+    b, h, w, c = x.shape
+    y = torch.empty((b, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_upsample2x_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "upsample2x")
+    return y
+
+
+def im2col_s2(x):
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float16
+    b, h, w, c = x.shape
+    y = torch.empty((b, h // 2, w // 2, 9 * c), device=x.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_im2col_s2_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "im2col_s2")
+    return y
+
+
+def cast_transpose(src, batch, rows, cols, out=None):
+    """fp32 [batch, rows, cols] -> fp16 [batch, cols, rows]"""
+    _require_cuda(src)
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.numel() == batch * rows * cols
+    if out is None:
+        out = torch.empty((batch, cols, rows), device=src.device, dtype=torch.float16)
+    check(_lib.load().ctrlora_cast_transpose_f32_to_f16(_dp(src), _dp(out), batch, rows, cols, _sp()), "cast_transpose")
+    return out
+
+
+def ddim_update(x, e_cond, e_uncond, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise=None, temperature=1.0,
+                stats=None):
+    """One DDIM update (cldm/ddim_hacked.py:190-231). fp32 [B,C,H,W] contiguous tensors; returns (x_prev, pred_x0)."""
+    _require_cuda(x, e_cond, e_uncond, noise)
+    for t in (x, e_cond, e_uncond, noise):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape)
+    x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    b = x.shape[0]
+    check(_lib.load().ctrlora_ddim_update(_dp(x), _dp(e_cond), _dp(e_uncond), _dp(noise), _dp(x_prev), _dp(pred_x0),
+                                          _dp(stats), b, x[0].numel(), float(cfg_scale), float(a_t), float(a_prev),
+                                          float(sigma_t), float(sqrt_one_minus_at), float(temperature), _sp()),
+          "ddim_update")
+    return x_prev, pred_x0

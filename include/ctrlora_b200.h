@@ -61,8 +61,10 @@ typedef struct ctrlora_gemm_args {
     const float* bias;      /* [n] ([2n] for GEGLU) or NULL */
     const float* rowbias;   /* [images, n] fp32 or NULL */
     int rows_per_img;       /* rows per image for rowbias / transposed stores; 0 = a_h * a_w */
-    const void* residual;   /* fp16 [M, ldr] added after scaling, or NULL */
+    int rowbias_ld;         /* row stride of rowbias (0 = n): lets one batched time-embedding GEMV feed every ResBlock */
+    const void* residual;   /* [M, ldr] added after scaling, or NULL; fp16 unless residual_f32 */
     int ldr;
+    int residual_f32;
     float out_scale;        /* applied to (acc + bias + rowbias) */
     int head_dim, tok_pad;  /* for transposed stores */
     int bf16;               /* must be 0 (fp16 operands) in this ABI version */
@@ -73,6 +75,61 @@ int ctrlora_gemm_f16(const ctrlora_gemm_args* args, void* stream);
 /* Bring-up / bisecting twin of ctrlora_gemm_f16 on the CUDA cores (same arguments, same results up to fp32
  * summation order).  Only the tests call it. */
 int ctrlora_gemm_f16_simt(const ctrlora_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over pixel-major fp16, fp32 statistics, optionally over the channel concatenation
+ * [x1 (+ add1_scale*add1) | x2 (+ add2_scale*add2)].
+ * replaces  GroupNorm32 + SiLU              ldm/modules/diffusionmodules/util.py:202-219, openaimodel.py:190-197,221-231,726-730
+ *           Normalize (eps 1e-6)            ldm/modules/attention.py:88-89,327
+ *           h += control.pop(); cat([h, hs.pop() + control.pop()], 1)    cldm/cldm.py:34-42
+ */
+typedef struct ctrlora_groupnorm_args {
+    const void* x1; const void* add1; float add1_scale; int c1; long long ld1;
+    const void* x2; const void* add2; float add2_scale; int c2; long long ld2;   /* x2 = NULL: single source */
+    int batch, hw, groups;
+    const float* gamma; const float* beta; float eps; int silu;
+    void* y;          /* fp16 [batch*hw, c1+c2] */
+    void* raw_out;    /* optional fp16 [batch*hw, c1+c2]: the concatenated (and summed) input itself, or NULL */
+    void* stats_ws;   /* fp32 workspace [batch * groups * 2] */
+} ctrlora_groupnorm_args;
+int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* args, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5 in the reference: ldm/modules/attention.py:263-265), fp16 in/out. */
+int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, int rows, int cols,
+                          const float* gamma, const float* beta, float eps, void* stream);
+
+/* Fused attention forward: out[b, i, h*d:(h+1)*d] = softmax_j(q_i . k_j * d^-1/2) v_j   (fp32 logits / softmax).
+ * replaces CrossAttention.forward   ldm/modules/attention.py:163-194 (and MemoryEfficientCrossAttention :197-243).
+ * q [batch, nq, heads*d] (row stride ldq), k [batch, nk, heads*d] (ldk), vt = V transposed [batch, heads, d, nk_pad]. */
+int ctrlora_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt, int nk_pad,
+                          void* out, long long ldo, int batch, int heads, int nq, int nk, int head_dim, void* stream);
+
+/* Module-boundary layout/dtype conversion (the reference's tensors are NCHW fp32). */
+int ctrlora_nchw_f32_to_nhwc_f16(const float* src, void* dst, int batch, int channels, int hw, int c_pad, void* stream);
+int ctrlora_nhwc_to_nchw_f32(const void* src, int src_is_f32, long long ld, float* dst, int batch, int channels, int hw,
+                             void* stream);
+
+/* timestep_embedding   ldm/modules/diffusionmodules/util.py:154-174: out[b] = [cos(t_b * f) | sin(t_b * f)];
+ * freqs (fp32 [half]) are computed on the host exactly as the reference does; t is int64. */
+int ctrlora_timestep_embedding(const long long* t, const float* freqs, float* out, int batch, int half, void* stream);
+
+/* y = act_out(act_in(x) W^T + b) for M = batch rows, fp32 activations, fp16 weights [n, k].
+ * replaces time_embed (Linear-SiLU-Linear, openaimodel.py:526-531) and every ResBlock emb_layers (SiLU-Linear, :208-215). */
+int ctrlora_small_linear(const float* x, int ldx, const void* w, const float* bias, float* y, int ldy, int rows, int n,
+                         int k, int silu_in, int silu_out, void* stream);
+
+/* F.interpolate(scale_factor=2, mode='nearest')   openaimodel.py:115 */
+int ctrlora_upsample2x_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
+/* gather for Downsample's conv3x3 stride 2 pad 1 (openaimodel.py:148-159): dst [batch, h/2, w/2, 9, channels] */
+int ctrlora_im2col_s2_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
+/* weight preparation: fp32 [batch, rows, cols] -> fp16 [batch, cols, rows] */
+int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, long long batch, int rows, int cols, void* stream);
+
+/* DDIM update in one pass   cldm/ddim_hacked.py:190-192 (CFG, e_uncond may be NULL), :208-231 (pred_x0, x_prev).
+ * fp32, round-to-nearest ops in the reference's order. stats (optional, [batch]) receives sum(x_prev^2) per image. */
+int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise, float* x_prev,
+                        float* pred_x0, float* stats, int batch, int per_image, float cfg_scale, float a_t, float a_prev,
+                        float sigma_t, float sqrt_one_minus_at, float temperature, void* stream);
 
 #ifdef __cplusplus
 }

@@ -132,10 +132,10 @@ def sequential_block(sd, p, x, emb, context, heads):
     return x
 
 
-def time_embed(sd, p, t, model_channels):
+def time_embed(sd, t, model_channels):
     """time_embed = Linear -> SiLU -> Linear, openaimodel.py:526-531 / cldm/cldm.py:131-136."""
     e = timestep_embedding(t, model_channels)
-    return linear(sd, p + ".time_embed.2", F.silu(linear(sd, p + ".time_embed.0", e)))
+    return linear(sd, "time_embed.2", F.silu(linear(sd, "time_embed.0", e)))
 
 
 def _sub(sd, prefix):
@@ -147,7 +147,7 @@ def _sub(sd, prefix):
 def controlnet_forward(sd, hint, t, context, heads, model_channels):
     """ControlNetFinetune.forward, cldm/cldm_ctrlora_finetune.py:40-54 (the 4-channel hint latent goes straight into
     input_blocks; input_hint_block is deleted at :19).  `sd` holds keys relative to control_model."""
-    emb = time_embed(sd, "", t, model_channels) if "time_embed.0.weight" in sd else None
+    emb = time_embed(sd, t, model_channels)
     outs, h = [], hint.float()
     for i in range(_num_children(sd, "input_blocks")):
         h = sequential_block(sd, f"input_blocks.{i}", h, emb, context, heads)
@@ -161,7 +161,7 @@ def unet_forward(sd, x, t, context, heads, model_channels, control=None, only_mi
     """ControlledUnetModel.forward, cldm/cldm.py:22-45.  `control` (list of 13) is consumed by pop() like the
     reference; `sd` holds keys relative to model.diffusion_model."""
     hs = []
-    emb = time_embed(sd, "", t, model_channels)
+    emb = time_embed(sd, t, model_channels)
     h = x.float()
     for i in range(_num_children(sd, "input_blocks")):
         h = sequential_block(sd, f"input_blocks.{i}", h, emb, context, heads)

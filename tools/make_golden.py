@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) in this container.
+
+    python tools/make_golden.py            # tiny config (committed fixture, ~300 KB)
+    python tools/make_golden.py --full     # SD1.5-size eps for one image (committed fixture, ~70 KB; takes minutes)
+
+The reference cannot travel to the GPU box; these fixtures can.  Weights/inputs are regenerated from names by
+oracle/synth.py, so the fixtures hold only key/shape lists and outputs.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import synth  # noqa: E402
+from tools import ref_shims  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def build_reference(yaml_path, seed):
+    ref_shims.install()
+    from cldm.model import create_model  # the reference's own factory (cldm/model.py:24-28)
+    torch.manual_seed(0)
+    model = create_model(yaml_path)
+    model.eval()
+    for sub, prefix in ((model.control_model, "control_model."), (model.model.diffusion_model, "model.diffusion_model.")):
+        shapes = {k: tuple(v.shape) for k, v in sub.state_dict().items()}
+        sub.load_state_dict(synth.synth_state_dict(shapes, seed, prefix), strict=True)
+    return model
+
+
+def shapes_of(mod):
+    return {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+
+
+def tiny(seed=0):
+    yaml_path = os.path.join(GOLD, "tiny_finetune.yaml")
+    model = build_reference(yaml_path, seed)
+    cn, unet = model.control_model, model.model.diffusion_model
+    B, H = 2, 16
+    x = synth.synth_input("x", (B, 4, H, H), seed)
+    hint = synth.synth_input("hint", (B, 4, H, H), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 64), seed)
+    noise = synth.synth_input("noise", (B, 4, H, H), seed)
+    t = torch.tensor([981, 21], dtype=torch.long)
+    g = {"seed": seed, "B": B, "H": H, "t": t,
+         "control_shapes": shapes_of(cn), "unet_shapes": shapes_of(unet),
+         "control_key_order": list(cn.state_dict().keys()), "unet_key_order": list(unet.state_dict().keys())}
+
+    with torch.no_grad():
+        control = cn(hint=hint, timesteps=t, context=ctx)
+        g["control"] = [c.clone() for c in control]
+        g["eps"] = unet(x=x, timesteps=t, context=ctx, control=[c.clone() for c in control], only_mid_control=False)
+        g["eps_nocontrol"] = unet(x=x, timesteps=t, context=ctx, control=None, only_mid_control=False)
+        g["eps_midonly"] = unet(x=x, timesteps=t, context=ctx, control=[c.clone() for c in control], only_mid_control=True)
+        scales = [0.5 + 0.1 * i for i in range(13)]
+        g["control_scales"] = scales
+        g["eps_scaled"] = unet(x=x, timesteps=t, context=ctx, control=[c * s for c, s in zip(control, scales)],
+                               only_mid_control=False)
+        # apply_model through the reference's own method, VAE stage bypassed (parity boundary = post-VAE)
+        model.encode_first_stage = lambda h: h
+        model.get_first_stage_encoding = lambda h: h
+        g["eps_apply_model"] = model.apply_model(x, t, {"c_crossattn": [ctx], "c_concat": [hint]})
+
+    # training step: q_sample -> apply_model -> loss -> grads of the optimizer's parameter set
+    x_noisy = model.q_sample(x_start=x, t=t, noise=noise)
+    g["x_noisy"] = x_noisy.clone()
+    for p in model.parameters():
+        p.grad = None
+    eps = model.apply_model(x_noisy, t, {"c_crossattn": [ctx], "c_concat": [hint]})
+    loss_simple = model.get_loss(eps, noise, mean=False).mean([1, 2, 3])
+    loss = loss_simple.mean()
+    loss.backward()
+    g["train_eps"] = eps.detach().clone()
+    g["loss"] = loss.detach().clone()
+    names = []
+    for n, p in cn.named_parameters():  # the filter of configure_optimizers (cldm_ctrlora_finetune.py:88-100)
+        if "lora_layer" in n or "zero_convs" in n or "middle_block_out" in n or "norm" in n:
+            names.append(n)
+    g["trainable_names"] = names
+    grads = dict(cn.named_parameters())
+    g["grad_norms"] = {n: grads[n].grad.norm().item() for n in names}
+    keep = [n for n in names if n.startswith(("zero_convs.0.", "middle_block_out", "input_blocks.1.1.norm",
+                                               "input_blocks.1.1.transformer_blocks.0.attn1.to_q.lora_layer",
+                                               "input_blocks.1.1.transformer_blocks.0.norm1",
+                                               "middle_block.1.transformer_blocks.0.ff.net.2.lora_layer",
+                                               "time_embed.0.lora_layer", "input_blocks.4.0.emb_layers.1.lora_layer"))]
+    g["grads"] = {n: grads[n].grad.clone() for n in keep}
+
+    # schedules / DDIM (bit-exact material)
+    from cldm.ddim_hacked import DDIMSampler
+    from ldm.modules.diffusionmodules.util import make_ddim_timesteps, timestep_embedding
+    g["betas"] = model.betas.clone()
+    g["alphas_cumprod"] = model.alphas_cumprod.clone()
+    g["alphas_cumprod_prev"] = model.alphas_cumprod_prev.clone()
+    g["sqrt_alphas_cumprod"] = model.sqrt_alphas_cumprod.clone()
+    g["sqrt_one_minus_alphas_cumprod"] = model.sqrt_one_minus_alphas_cumprod.clone()
+    g["ddim_timesteps"] = {S: make_ddim_timesteps("uniform", S, 1000, verbose=False) for S in (50, 20, 10, 2)}
+    g["timestep_embedding"] = timestep_embedding(torch.tensor([0, 1, 21, 500, 981, 999]), 32)
+    g["timestep_embedding_320"] = timestep_embedding(torch.tensor([981, 21]), 320)
+    sampler = DDIMSampler(model)
+    sampler.register_buffer = lambda name, attr: setattr(sampler, name, attr)  # reference hard-codes .to('cuda')
+    for eta in (0.0, 0.5):
+        sampler.make_schedule(50, ddim_eta=eta, verbose=False)
+        g[f"ddim_tables_eta{eta}"] = {
+            "sigmas": np.asarray(sampler.ddim_sigmas), "alphas": np.asarray(sampler.ddim_alphas),
+            "alphas_prev": np.asarray(sampler.ddim_alphas_prev),
+            "sqrt_one_minus_alphas": np.asarray(sampler.ddim_sqrt_one_minus_alphas)}
+    # one p_sample_ddim with CFG 7.5 through the reference sampler (eta 0), tiny model as the eps predictor
+    sampler.make_schedule(50, ddim_eta=0.0, verbose=False)
+    uc_ctx = synth.synth_input("uc_ctx", (B, 77, 64), seed)
+    cond = {"c_crossattn": [ctx], "c_concat": [hint]}
+    ucond = {"c_crossattn": [uc_ctx], "c_concat": [hint]}
+    ts = torch.full((B,), 981, dtype=torch.long)
+    with torch.no_grad():
+        x_prev, pred_x0 = sampler.p_sample_ddim(x, cond, ts, index=49, unconditional_guidance_scale=7.5,
+                                                unconditional_conditioning=ucond)
+        g["ddim_step"] = {"x_prev": x_prev, "pred_x0": pred_x0, "index": 49, "scale": 7.5}
+        # 4-step sampling loop end-to-end (x_T given): exercises the index/timestep bookkeeping
+        samples, inter = sampler.sample(4, B, (4, H, H), cond, verbose=False, eta=0.0, x_T=x,
+                                        unconditional_guidance_scale=7.5, unconditional_conditioning=ucond,
+                                        log_every_t=1)
+        g["ddim_sample4"] = {"samples": samples, "pred_x0_last": inter["pred_x0"][-1], "n_inter": len(inter["x_inter"])}
+
+    # LoRA layer semantics (cldm/lora.py)
+    from cldm.lora import LoRACompatibleLinear, LoRALinearLayer
+    lin = LoRACompatibleLinear(16, 24, lora_layer=LoRALinearLayer(16, 24, rank=4))
+    lsd = synth.synth_state_dict({k: tuple(v.shape) for k, v in lin.state_dict().items()}, seed, "loratest.")
+    lin.load_state_dict(lsd)
+    xin = synth.synth_input("loratest", (3, 16), seed)
+    with torch.no_grad():
+        y_unfused = lin(xin)
+        lin._fuse_lora(lora_scale=0.7)
+        w_fused = lin.weight.clone()
+        y_fused = lin(xin)
+        lin._unfuse_lora()
+        w_unfused = lin.weight.clone()
+    g["lora"] = {"shapes": {k: tuple(v.shape) for k, v in lsd.items()}, "y": y_unfused, "w_fused_0.7": w_fused,
+                 "y_fused_0.7": y_fused, "w_unfused": w_unfused}
+    out = os.path.join(GOLD, "tiny_finetune_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
+def full(seed=0):
+    """One SD1.5-size apply_model (post-VAE) on the reference: rank-128 finetune config, B=1."""
+    t0 = time.time()
+    yaml_path = os.path.join(ref_shims.REFERENCE_ROOT, "configs", "ctrlora_finetune_sd15_rank128.yaml")
+    ref_shims.install()
+    from omegaconf import OmegaConf
+    from ldm.util import instantiate_from_config
+    cfg = OmegaConf.load(yaml_path).model.params
+    with torch.device("meta"):  # skip the 160 s of default init over 1.33 B params
+        cn = instantiate_from_config(cfg.control_stage_config)
+        unet = instantiate_from_config(cfg.unet_config)
+    cn.eval(), unet.eval()
+    for sub, prefix in ((cn, "control_model."), (unet, "model.diffusion_model.")):
+        shapes = {k: tuple(v.shape) for k, v in sub.state_dict().items()}
+        sub.to_empty(device="cpu")
+        sub.load_state_dict(synth.synth_state_dict(shapes, seed, prefix), strict=True)
+    print("built in", time.time() - t0)
+    B = 1
+    x = synth.synth_input("x", (B, 4, 64, 64), seed)
+    hint = synth.synth_input("hint", (B, 4, 64, 64), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 768), seed)
+    t = torch.tensor([501], dtype=torch.long)
+    g = {"seed": seed, "t": t, "control_shapes": shapes_of(cn), "unet_shapes": shapes_of(unet)}
+    with torch.no_grad():
+        control = cn(hint=hint, timesteps=t, context=ctx)
+        g["control_norms"] = [c.norm().item() for c in control]
+        g["control_12"] = control[12].clone()
+        g["control_0_slice"] = control[0][:, :8].clone()
+        g["eps"] = unet(x=x, timesteps=t, context=ctx, control=[c.clone() for c in control], only_mid_control=False)
+    out = os.path.join(GOLD, "sd15_rank128_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB", "in", time.time() - t0, "s")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    full() if a.full else tiny()

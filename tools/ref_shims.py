@@ -51,7 +51,12 @@ def install():
                 return _wrap(obj)
 
         m.OmegaConf, m.ListConfig = OmegaConf, ListConfig
+        m.__path__ = []
+        lc = types.ModuleType("omegaconf.listconfig")
+        lc.ListConfig = ListConfig
+        m.listconfig = lc
         sys.modules["omegaconf"] = m
+        sys.modules["omegaconf.listconfig"] = lc
     if "pytorch_lightning" not in sys.modules:
         pl = types.ModuleType("pytorch_lightning")
 
