@@ -112,8 +112,8 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     for ad, ref in ((add1, x1), (add2, x2)):
         if ad is not None:
             assert ad.shape == ref.shape and ad.stride() == ref.stride() and ad.dtype == torch.float16
-    C = c1 + c2
-    y = torch.empty((b, h, w, C), device=x1.device, dtype=torch.float16)
+    ctot = c1 + c2
+    y = torch.empty((b, h, w, ctot), device=x1.device, dtype=torch.float16)
     raw = torch.empty_like(y) if want_raw else None
     if stats_ws is None:
         stats_ws = torch.empty(b * groups * 2, device=x1.device, dtype=torch.float32)
@@ -121,7 +121,7 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     a.x1, a.add1, a.add1_scale, a.c1, a.ld1 = _dp(x1), _dp(add1), float(add1_scale), c1, ld1
     a.x2, a.add2, a.add2_scale, a.c2, a.ld2 = _dp(x2), _dp(add2), float(add2_scale), c2, ld2
     a.batch, a.hw, a.groups = b, h * w, groups
-    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == C
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == ctot
     a.gamma, a.beta, a.eps, a.silu = _dp(gamma), _dp(beta), float(eps), int(silu)
     a.y, a.raw_out, a.stats_ws = _dp(y), _dp(raw), _dp(stats_ws)
     check(_lib.load().ctrlora_groupnorm_f16(C.addressof(a), _sp()), "ctrlora_groupnorm_f16")

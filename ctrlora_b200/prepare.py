@@ -1,0 +1,117 @@
+"""Kernel-layout weight copies (fp16, K-major, tap-major convs, LoRA folded in), cached per module and
+re-derived whenever a source parameter changes (torch's `_version` counter / a new storage).
+
+The fp32 nn.Parameters keep the reference's names and shapes, so `load_state_dict(strict=True)`, the optimizer
+filters and the checkpoint tooling see the reference's state dict; these copies are derived data.
+"""
+import torch
+
+from . import ops
+
+
+def _ver(*params):
+    return tuple((p.data_ptr(), p._version, tuple(p.shape)) if p is not None else None for p in params)
+
+
+class PrepCache:
+    """`get(key, params, builder)` returns builder() and re-runs it only when one of `params` changed."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, params, builder):
+        ver = _ver(*params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        self._store[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+def _f32c(p):
+    t = p.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+def linear_weight(weight):
+    """nn.Linear weight fp32 [N, K] -> fp16 [N, 1, K]"""
+    n, k = weight.shape
+    return ops.cast_transpose(_f32c(weight), n * k, 1, 1).view(n, 1, k)
+
+
+def conv_weight(weight, pad_in=None, pad_out=None):
+    """nn.Conv2d weight fp32 [Cout, Cin, kh, kw] -> fp16 [Cout(pad), kh*kw, Cin(pad)] (tap-major, channel-minor)."""
+    co, ci, kh, kw = weight.shape
+    w = ops.cast_transpose(_f32c(weight), co, ci, kh * kw)  # [Cout, taps, Cin]
+    if pad_in or pad_out:
+        full = torch.zeros((pad_out or co, kh * kw, pad_in or ci), device=w.device, dtype=torch.float16)
+        full[:co, :, :ci] = w
+        w = full
+    return w
+
+
+def lora_folded_weight(weight, down, up, scale=1.0):
+    """W' = W + scale * up @ down as fp16 [N, 1, K]  (cldm/lora.py:250 `_fuse_lora`, evaluated in fp32 accumulate).
+
+    One tcgen05 GEMM: A = up [N, r], B = down^T [K, r], epilogue adds the fp32 master W.  Cost 2*N*K*r flop, once per
+    weight version (per optimizer step in training, once per checkpoint in sampling) instead of two skinny GEMMs and an
+    add per forward call (cldm/lora.py:285-291)."""
+    n, k = weight.shape
+    r = down.shape[0]
+    up16 = ops.cast_transpose(_f32c(up), n * r, 1, 1).view(n, r)
+    down_t = ops.cast_transpose(_f32c(down), 1, r, k).view(k, 1, r)  # [K, r]
+    if r % 8:  # TMA needs 16-byte rows: zero-pad the rank
+        rp = (r + 7) // 8 * 8
+        u2 = torch.zeros((n, rp), device=up16.device, dtype=torch.float16)
+        u2[:, :r] = up16
+        d2 = torch.zeros((k, 1, rp), device=up16.device, dtype=torch.float16)
+        d2[:, :, :r] = down_t
+        up16, down_t = u2, d2
+    out = torch.empty((n, k), device=weight.device, dtype=torch.float16)
+    ops.gemm(up16, down_t, residual=_f32c(weight), out_scale=scale, out=out)
+    return out.view(n, 1, k)
+
+
+def effective_linear_weight(linear):
+    """fp16 [N,1,K] weight of an nn.Linear or a LoRACompatibleLinear (LoRA folded when a lora_layer is attached)."""
+    lora = getattr(linear, "lora_layer", None)
+    if lora is None:
+        return linear_weight(linear.weight)
+    scale = 1.0
+    if getattr(lora, "network_alpha", None) is not None:
+        scale = lora.network_alpha / lora.rank  # cldm/lora.py:77-78
+    return lora_folded_weight(linear.weight, lora.down.weight, lora.up.weight, scale * getattr(linear, "_lora_scale", 1.0))
+
+
+def linear_params(linear):
+    """the parameters whose change invalidates effective_linear_weight(linear)"""
+    lora = getattr(linear, "lora_layer", None)
+    ps = [linear.weight]
+    if lora is not None:
+        ps += [lora.down.weight, lora.up.weight]
+    return ps
+
+
+def bias_f32(p):
+    return None if p is None else _f32c(p)
+
+
+def effective(module):
+    """For the reference's Switchable* layers (cldm/switchable.py): the swapped-in inner layer's parameters are the
+    live ones; any other module is its own effective layer."""
+    inner = getattr(module, "norm_layer", None)
+    if inner is None:
+        inner = getattr(module, "conv_layer", None)
+    return module if inner is None else inner
+
+
+def lora_key(*linears):
+    """cache-key component identifying which LoRA set is attached (switch_lora re-points `lora_layer`)"""
+    return tuple(id(getattr(lin, "lora_layer", None)) for lin in linears)

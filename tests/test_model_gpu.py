@@ -1,0 +1,191 @@
+"""End-to-end parity of the CUDA hot path (through the drop-in module API and the C ABI) against
+  (1) the golden fixtures produced by the unmodified reference (tests/golden/*.pt), and
+  (2) the CPU oracle on freshly seeded inputs at a second, wider configuration.
+
+Metric: norm-relative error ||got - ref||_2 / ||ref||_2 per output tensor.  The reference computes in fp32; this path
+computes with fp16 operands / fp32 accumulation (north_star: "within 1e-3 relative fp16").  Tolerances are written
+next to each assert; the measured values are printed with -s.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+pytestmark = pytest.mark.gpu
+
+
+def rel(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).norm() / (ref.norm() + 1e-20)).item()
+
+
+def build(yaml_path, control_shapes, unet_shapes, seed):
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from cldm.model import create_model
+    from oracle import synth
+    model = create_model(yaml_path, init_weights=False)
+    model.control_model.load_state_dict(synth.synth_state_dict(control_shapes, seed, "control_model."), strict=True)
+    model.model.diffusion_model.load_state_dict(synth.synth_state_dict(unet_shapes, seed, "model.diffusion_model."),
+                                                strict=True)
+    return model.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def g():
+    return torch.load(os.path.join(GOLD, "tiny_finetune_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def tiny(g):
+    return build(os.path.join(GOLD, "tiny_finetune.yaml"), g["control_shapes"], g["unet_shapes"], g["seed"])
+
+
+def tiny_inputs(g):
+    from oracle import synth
+    B, H, seed = g["B"], g["H"], g["seed"]
+    mk = lambda n, s: synth.synth_input(n, s, seed).cuda()
+    return mk("x", (B, 4, H, H)), mk("hint", (B, 4, H, H)), mk("ctx", (B, 77, 64)), mk("uc_ctx", (B, 77, 64))
+
+
+def test_tiny_control_and_eps_vs_reference_golden(g, tiny):
+    x, hint, ctx, _ = tiny_inputs(g)
+    t = g["t"].cuda()
+    with torch.no_grad():
+        control = tiny.control_model(hint=hint, timesteps=t, context=ctx)
+        assert len(control) == 13
+        errs = []
+        for c, ref in zip(control, g["control"]):
+            assert tuple(c.shape) == tuple(ref.shape)
+            errs.append(rel(c, ref))
+        print("control residual rel errors:", ["%.2e" % e for e in errs])
+        assert max(errs) < 3e-3
+        unet = tiny.model.diffusion_model
+        e = {
+            "eps": rel(unet(x=x, timesteps=t, context=ctx, control=list(control)), g["eps"]),
+            "eps_nocontrol": rel(unet(x=x, timesteps=t, context=ctx, control=None), g["eps_nocontrol"]),
+            "eps_midonly": rel(unet(x=x, timesteps=t, context=ctx, control=list(control), only_mid_control=True),
+                               g["eps_midonly"]),
+        }
+        cl = list(control)
+        unet(x=x, timesteps=t, context=ctx, control=cl)
+        assert cl == []  # consumed by pop() like the reference (cldm/cldm.py:35,41)
+        cond = {"c_crossattn": [ctx], "c_concat": [hint]}
+        e["apply_model"] = rel(tiny.apply_model(x, t, cond), g["eps_apply_model"])
+        tiny.control_scales = list(g["control_scales"])
+        e["scaled"] = rel(tiny.apply_model(x, t, cond), g["eps_scaled"])
+        tiny.control_scales = [1.0] * 13
+    print("eps rel errors:", {k: "%.2e" % v for k, v in e.items()})
+    assert max(e.values()) < 3e-3
+    # the LoRA / control path is really exercised: removing the control changes eps far beyond the tolerance
+    assert rel(g["eps_nocontrol"], g["eps"]) > 0.05
+
+
+def test_tiny_ddim_step_and_loop_vs_reference_golden(g, tiny):
+    from cldm.ddim_hacked import DDIMSampler
+    x, hint, ctx, uc = tiny_inputs(g)
+    cond = {"c_crossattn": [ctx], "c_concat": [hint]}
+    ucond = {"c_crossattn": [uc], "c_concat": [hint]}
+    B = g["B"]
+    for batched, graph in ((True, True), (False, False), (True, False)):
+        s = DDIMSampler(tiny, batched_cfg=batched, use_cuda_graph=graph)
+        s.make_schedule(50, ddim_eta=0.0, verbose=False)
+        ts = torch.full((B,), 981, dtype=torch.long, device="cuda")
+        x_prev, pred_x0 = s.p_sample_ddim(x, cond, ts, index=49, unconditional_guidance_scale=7.5,
+                                          unconditional_conditioning=ucond)
+        e1, e2 = rel(x_prev, g["ddim_step"]["x_prev"]), rel(pred_x0, g["ddim_step"]["pred_x0"])
+        print(f"ddim step (batched={batched}, graph={graph}): x_prev {e1:.2e} pred_x0 {e2:.2e}")
+        assert e1 < 3e-3 and e2 < 1e-2  # pred_x0 divides the eps error by sqrt(a_t) ~ 0.07 at t = 981
+        samples, inter = s.sample(4, B, (4, g["H"], g["H"]), cond, verbose=False, eta=0.0, x_T=x,
+                                  unconditional_guidance_scale=7.5, unconditional_conditioning=ucond, log_every_t=1)
+        e3 = rel(samples, g["ddim_sample4"]["samples"])
+        print(f"  4-step sample: {e3:.2e}")
+        assert e3 < 1e-2 and len(inter["x_inter"]) == g["ddim_sample4"]["n_inter"]
+
+
+MID_YAML = """
+model:
+  target: cldm.cldm_ctrlora_finetune.ControlFinetuneLDM
+  params:
+    linear_start: 0.00085
+    linear_end: 0.0120
+    timesteps: 1000
+    first_stage_key: jpg
+    cond_stage_key: txt
+    control_key: hint
+    image_size: 32
+    channels: 4
+    conditioning_key: crossattn
+    scale_factor: 0.18215
+    use_ema: false
+    only_mid_control: false
+    control_stage_config:
+      target: cldm.cldm_ctrlora_finetune.ControlNetFinetune
+      params: {image_size: 32, in_channels: 4, hint_channels: 3, model_channels: 64, attention_resolutions: [4, 2, 1],
+               num_res_blocks: 2, channel_mult: [1, 2, 4, 4], num_heads: 8, use_spatial_transformer: true,
+               transformer_depth: 1, context_dim: 128, use_checkpoint: true, legacy: false, ft_with_lora: true,
+               lora_rank: 16, norm_trainable: true}
+    unet_config:
+      target: cldm.cldm.ControlledUnetModel
+      params: {image_size: 32, in_channels: 4, out_channels: 4, model_channels: 64, attention_resolutions: [4, 2, 1],
+               num_res_blocks: 2, channel_mult: [1, 2, 4, 4], num_heads: 8, use_spatial_transformer: true,
+               transformer_depth: 1, context_dim: 128, use_checkpoint: true, legacy: false}
+    first_stage_config: __is_first_stage__
+    cond_stage_config: __is_unconditional__
+"""
+
+
+def test_mid_config_vs_cpu_oracle(tmp_path):
+    """model_channels 64, 8 heads (d = 8/16/32), 32x32 latent, rank 16, batch 3, seeded inputs: CUDA path vs the oracle."""
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from cldm.model import create_model
+    from oracle import ctrlora_oracle as O
+    from oracle import synth
+    p = tmp_path / "mid.yaml"
+    p.write_text(MID_YAML)
+    model = create_model(str(p), init_weights=False)
+    seed = 3
+    for sub, prefix in ((model.control_model, "control_model."), (model.model.diffusion_model, "model.diffusion_model.")):
+        shapes = {k: tuple(v.shape) for k, v in sub.state_dict().items()}
+        sub.load_state_dict(synth.synth_state_dict(shapes, seed, prefix))
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    B = 3
+    x, hint = synth.synth_input("x", (B, 4, 32, 32), seed), synth.synth_input("hint", (B, 4, 32, 32), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 128), seed)
+    t = torch.tensor([999, 500, 0])
+    with torch.no_grad():
+        ref = O.apply_model(sd, x, t, ctx, hint, 8, 64)
+        got = model.apply_model(x.cuda(), t.cuda(), {"c_crossattn": [ctx.cuda()], "c_concat": [hint.cuda()]})
+    e = rel(got, ref)
+    print(f"mid config apply_model rel err {e:.2e}")
+    assert e < 3e-3
+
+
+@pytest.mark.skipif(os.environ.get("CTRLORA_SKIP_FULL") == "1", reason="CTRLORA_SKIP_FULL=1")
+def test_sd15_rank128_vs_reference_golden():
+    """Full SD1.5 + ControlNet rank-128 apply_model, B = 1, against eps produced by the unmodified reference."""
+    g = torch.load(os.path.join(GOLD, "sd15_rank128_golden.pt"), weights_only=False)
+    cfg = os.path.join(ROOT, "configs", "ctrlora_finetune_sd15_rank128.yaml")
+    model = build(cfg, g["control_shapes"], g["unet_shapes"], g["seed"])
+    from oracle import synth
+    x = synth.synth_input("x", (1, 4, 64, 64), g["seed"]).cuda()
+    hint = synth.synth_input("hint", (1, 4, 64, 64), g["seed"]).cuda()
+    ctx = synth.synth_input("ctx", (1, 77, 768), g["seed"]).cuda()
+    t = g["t"].cuda()
+    with torch.no_grad():
+        control = model.control_model(hint=hint, timesteps=t, context=ctx)
+        norms = [c.float().norm().item() for c in control]
+        nerr = max(abs(a - b) / b for a, b in zip(norms, g["control_norms"]))
+        e12 = rel(control[12], g["control_12"])
+        e0 = rel(control[0][:, :8], g["control_0_slice"])
+        eps = model.model.diffusion_model(x=x, timesteps=t, context=ctx, control=list(control))
+    e = rel(eps, g["eps"])
+    print(f"SD1.5 rank128: control norm err {nerr:.2e}, control[12] {e12:.2e}, control[0][:8] {e0:.2e}, eps {e:.2e}")
+    assert e0 < 3e-3 and e12 < 5e-3 and e < 5e-3
