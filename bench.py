@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the CtrLoRA denoising hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1]): SD1.5 UNet + ControlNet (LoRA rank 128), 512x512 (latent 4x64x64), batch 4,
+DDIM with classifier-free guidance 7.5.  One "step" = one DDIM step = eps for the conditional and unconditional
+branches (one batch-8 pass of ControlNet + UNet) + the fused DDIM update.  Weights are random (no checkpoints
+offline), inputs synthetic.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                           # the reference's algorithm on the host CPU (oracle port)
+
+N > 1 (torchrun): sampling does not exchange anything between images, so ranks are independent replicas
+("replicas only"); value = N * K steps / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, LATENT, CTX_TOKENS, CTX_DIM, CFG_SCALE = 4, 64, 77, 768, 7.5
+CONFIG = os.path.join(ROOT, "configs", "ctrlora_finetune_sd15_rank128.yaml")
+GF_PER_IMAGE_PASS = 1103.4  # algorithmic forward GFLOP of ControlNet(r=128) + UNet per image
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def random_weights_(model, seed):
+    """Variance-preserving random weights written straight on the GPU (same scale rules as oracle/synth.py)."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            g = torch.randn(p.shape, device=p.device, generator=gen)
+            if "lora_layer.down" in name:
+                g *= 1.0 / p.shape[0]
+            elif "lora_layer.up" in name:
+                g *= 0.05
+            elif p.dim() >= 2:
+                g *= (p[0].numel()) ** -0.5
+            elif name.endswith(".weight"):
+                g = 1.0 + 0.1 * g
+            else:
+                g *= 0.1
+            p.copy_(g)
+
+
+def build_model(device, seed=0):
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from cldm.model import create_model
+    model = create_model(CONFIG, init_weights=False)
+    model = model.to(device).eval()
+    random_weights_(model, seed)
+    return model
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows and self.rows[0][1].replace(".", "").isdigit() else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1412.1), d.get("hbm_gbs", 6569.6), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_pass(model_state, threads, n_images=1, seed=1):
+    """One apply_model of the reference's algorithm (oracle port) on the host cores; returns seconds."""
+    from oracle import ctrlora_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_images, 4, LATENT, LATENT, generator=g)
+    hint = torch.randn(n_images, 4, LATENT, LATENT, generator=g)
+    ctx = torch.randn(n_images, CTX_TOKENS, CTX_DIM, generator=g)
+    t = torch.full((n_images,), 501, dtype=torch.long)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.apply_model(model_state, x, t, ctx, hint, 8, 320)
+    return time.perf_counter() - t0
+
+
+def cpu_state_dict(seed=0):
+    """fp32 weights for the CPU oracle (same architecture, random values; generated on the host)."""
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from cldm.model import create_model
+    model = create_model(CONFIG, init_weights=False)
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    with torch.no_grad():
+        for name, p in model.state_dict().items():
+            if not name.startswith(("control_model.", "model.diffusion_model.")):
+                continue
+            v = torch.randn(p.shape, generator=g)
+            if "lora_layer.down" in name:
+                v *= 1.0 / p.shape[0]
+            elif "lora_layer.up" in name:
+                v *= 0.05
+            elif p.dim() >= 2:
+                v *= (p[0].numel()) ** -0.5
+            elif name.endswith(".weight"):
+                v = 1.0 + 0.1 * v
+            else:
+                v *= 0.1
+            sd[name] = v
+    return sd
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference is a Python
+    tree that cannot travel to the GPU box), all host threads, same config/metric/unit.  One 'step' of this arm is a
+    bounded sample of the DDIM step: ONE of its 8 image passes (apply_model at batch 1)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sd = cpu_state_dict()
+    times = []
+    budget_s = 240.0
+    t_first = cpu_reference_pass(sd, threads)  # warm-up 1 (also sizes the run)
+    warm = max(0, args.warmup - 1)
+    steps = args.steps
+    if t_first * (warm + steps) > budget_s:  # keep the whole arm within a few minutes
+        warm = 0
+        steps = max(1, int(budget_s / t_first) - 1)
+    for _ in range(warm):
+        cpu_reference_pass(sd, threads)
+    for _ in range(steps):
+        times.append(cpu_reference_pass(sd, threads))
+    t_pass = sum(times) / len(times)
+    passes_per_step = 2 * BATCH
+    value = 1.0 / (t_pass * passes_per_step)
+    line = {"impl": "reference", "metric": "ddim_steps_per_sec", "value": value, "unit": "steps/s (batch 4, CFG)",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": t_pass * passes_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "steps/s (batch 4, CFG)", "cores": threads, "kind": "port",
+                             "sample": f"{steps} x one apply_model at batch 1 (1/8 of a DDIM step each), "
+                                       f"{t_pass:.2f} s per pass, extrapolated x8"},
+            "e2e": {"value": value, "unit": "steps/s (batch 4, CFG)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "configs[1]: SD1.5 UNet + ControlNet LoRA rank-128, DDIM step with CFG 7.5, batch 4, 512x512 "
+                        "(latent 4x64x64), 77x768 context; cond+uncond batched as one batch-8 pass",
+            "batch_per_gpu": BATCH, "cfg_scale": CFG_SCALE, "ddim_steps_schedule": 50,
+            "parallelism": f"replicas x{n}" if n > 1 else "single GPU",
+            "l2": "no flush needed: 2.7 GB of fp16 weights stream through the 126 MB L2 every step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from ctrlora_b200 import ops
+    from cldm.ddim_hacked import DDIMSampler  # noqa: E402  (dropin activated in build_model)
+    model = build_model(device, seed=rank)
+    from cldm.ddim_hacked import DDIMSampler  # noqa: F811
+    sampler = DDIMSampler(model, batched_cfg=True, use_cuda_graph=True)
+    sampler.make_schedule(50, ddim_eta=0.0, verbose=False)
+    S = len(sampler.ddim_timesteps)
+
+    gen = torch.Generator().manual_seed(100 + rank)
+    host = {"x": torch.randn(BATCH, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "hint": torch.randn(BATCH, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "ctx": torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=gen).pin_memory(),
+            "uc": torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=gen).pin_memory()}
+    dev = {k: v.to(device) for k, v in host.items()}
+    cond = {"c_crossattn": [dev["ctx"]], "c_concat": [dev["hint"]]}
+    ucond = {"c_crossattn": [dev["uc"]], "c_concat": [dev["hint"]]}
+
+    def step(i, x, c=cond, u=ucond):
+        index = S - 1 - (i % S)
+        ts = torch.full((BATCH,), int(sampler.ddim_timesteps[index]), device=device, dtype=torch.long)
+        return sampler.p_sample_ddim(x, c, ts, index=index, unconditional_guidance_scale=CFG_SCALE,
+                                     unconditional_conditioning=u)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- launches per step (counted on an un-graphed pass through the C ABI)
+    ops.LAUNCHES = 0
+    x = dev["x"]
+    for i in range(args.warmup):  # includes weight preparation, LoRA folding and the graph capture
+        x, _ = step(i, x)
+    torch.cuda.synchronize()
+    launches_per_step = ops.count_launches(lambda: step(0, dev["x"]), sampler)
+
+    # ---- (1) device-resident throughput
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    x = dev["x"]
+    for i in range(args.steps):
+        x, _ = step(i, x)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clk = clocks.stop()
+
+    # ---- (2) end to end through the public API with host buffers: H2D of the step's inputs, D2H of its result
+    out_host = torch.empty(BATCH, 4, LATENT, LATENT).pin_memory()
+    stats_host = torch.empty(BATCH).pin_memory()
+    h2d = sum(host[k].numel() * 4 for k in ("x", "hint", "ctx", "uc")) + BATCH * 8
+    d2h = out_host.numel() * 4 + stats_host.numel() * 4
+
+    def e2e_step(i):
+        d = {k: host[k].to(device, non_blocking=True) for k in ("x", "hint", "ctx", "uc")}
+        c = {"c_crossattn": [d["ctx"]], "c_concat": [d["hint"]]}
+        u = {"c_crossattn": [d["uc"]], "c_concat": [d["hint"]]}
+        xp, _ = step(i, d["x"], c, u)
+        out_host.copy_(xp, non_blocking=True)
+        stats_host.copy_(sampler.last_stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result before issuing the next step
+        host["x"].copy_(out_host)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events on an un-graphed step
+    gemm_stats = ops.profile_gemm(lambda: step(0, dev["x"]), sampler)
+
+    t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        value = world * args.steps / (ms_dev / 1e3)
+        e2e_value = world * args.steps / (ms_e2e / 1e3)
+        ach = gemm_stats["flops"] / (gemm_stats["ms"] * 1e-3) / 1e12 if gemm_stats["ms"] > 0 else 0.0
+        line = {"metric": "ddim_steps_per_sec", "value": value, "unit": "steps/s (batch 4, CFG)", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate)",
+                "data": "synthetic", "config": workload_config(world), "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": "steps/s (batch 4, CFG)", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches_per_step * args.steps,
+                "images_per_sec": value * BATCH,
+                "model_tflops": value / world * 2 * BATCH * GF_PER_IMAGE_PASS / 1e3,
+                "roofline": {"kernel": "gemm_tcgen05_kernel (all convs + linears of one step)", "bound": "tensor",
+                             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                             "peak_source": peak_src + ", sustained bf16/fp16 dense", "traffic": None,
+                             "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,
+                             "share_of_step": gemm_stats["ms"] / (ms_dev / args.steps)}}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sd = cpu_state_dict()
+            cpu_reference_pass(sd, threads)
+            tp = cpu_reference_pass(sd, threads)
+            v = 1.0 / (tp * 2 * BATCH)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s (batch 4, CFG)", "cores": threads, "kind": "port",
+                                    "sample": f"one apply_model at batch 1 (1/8 of a DDIM step) after one warm-up, "
+                                              f"{tp:.2f} s, extrapolated x8"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

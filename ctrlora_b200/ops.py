@@ -11,6 +11,48 @@ from . import _lib
 from ._lib import GemmArgs, check
 
 
+LAUNCHES = 0      # kernels launched through this module since the last reset (bench.py's gpu_launches)
+_GEMM_PROFILE = None  # list of (flops, start_event, end_event) while profile_gemm() is active
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ungraphed(fn, sampler):
+    old = getattr(sampler, "use_cuda_graph", False)
+    if sampler is not None:
+        sampler.use_cuda_graph = False
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        if sampler is not None:
+            sampler.use_cuda_graph = old
+
+
+def count_launches(fn, sampler=None):
+    """Kernel launches of one call of `fn` (run without CUDA-graph replay so every C-ABI call is seen)."""
+    global LAUNCHES
+    LAUNCHES = 0
+    _ungraphed(fn, sampler)
+    return LAUNCHES
+
+
+def profile_gemm(fn, sampler=None):
+    """Per-launch CUDA-event timing of every ctrlora_gemm_f16 launch inside `fn`: algorithmic flops and device ms."""
+    global _GEMM_PROFILE
+    _GEMM_PROFILE = []
+    try:
+        _ungraphed(fn, sampler)
+        recs = _GEMM_PROFILE
+    finally:
+        _GEMM_PROFILE = None
+    return {"launches": len(recs), "flops": float(sum(r[0] for r in recs)),
+            "ms": float(sum(r[1].elapsed_time(r[2]) for r in recs))}
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -87,6 +129,15 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
     args.out_scale, args.head_dim, args.tok_pad, args.bf16 = float(out_scale), head_dim, tok_pad, 0
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
+    _count()
+    if _GEMM_PROFILE is not None and not simt:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(C.addressof(args), _sp()), "ctrlora_gemm_f16")
+        e1.record()
+        ktot = ksize * ksize * c + (args.a2_c if a2 is not None else 0)
+        _GEMM_PROFILE.append((2.0 * M * n_rows * ktot, e0, e1))
+        return ret
     check(fn(C.addressof(args), _sp()), "ctrlora_gemm_f16")
     return ret
 
@@ -124,6 +175,7 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == ctot
     a.gamma, a.beta, a.eps, a.silu = _dp(gamma), _dp(beta), float(eps), int(silu)
     a.y, a.raw_out, a.stats_ws = _dp(y), _dp(raw), _dp(stats_ws)
+    _count(2)
     check(_lib.load().ctrlora_groupnorm_f16(C.addressof(a), _sp()), "ctrlora_groupnorm_f16")
     return (y, raw) if want_raw else y
 
@@ -134,6 +186,7 @@ def layernorm(x, gamma, beta, eps=1e-5):
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     y = torch.empty((x2.shape[0], cols), device=x.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_layernorm_f16(_dp(x2), x2.stride(0), _dp(y), cols, x2.shape[0], cols, _dp(gamma), _dp(beta),
                                             float(eps), _sp()), "ctrlora_layernorm_f16")
     return y.view(x.shape)
@@ -144,6 +197,7 @@ def attention(q, k, vt, batch, heads, nq, nk, head_dim, out=None):
     _require_cuda(q, k, vt)
     if out is None:
         out = torch.empty((batch * nq, heads * head_dim), device=q.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_attention_f16(_dp(q), q.stride(0), _dp(k), k.stride(0), _dp(vt), vt.shape[-1], _dp(out),
                                             out.stride(0), batch, heads, nq, nk, head_dim, _sp()),
           "ctrlora_attention_f16")
@@ -157,6 +211,7 @@ def nchw_to_nhwc_f16(x, c_pad=None):
     b, c, h, w = x.shape
     c_pad = c_pad or c
     y = torch.empty((b, h, w, c_pad), device=x.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_nchw_f32_to_nhwc_f16(_dp(x), _dp(y), b, c, h * w, c_pad, _sp()), "nchw_to_nhwc")
     return y
 
@@ -167,6 +222,7 @@ def nhwc_to_nchw_f32(x, channels=None):
     b, h, w, c, ld = _as_bhwc(x)
     channels = channels or c
     y = torch.empty((b, channels, h, w), device=x.device, dtype=torch.float32)
+    _count(1)
     check(_lib.load().ctrlora_nhwc_to_nchw_f32(_dp(x), int(x.dtype == torch.float32), ld, _dp(y), b, channels, h * w,
                                                _sp()), "nhwc_to_nchw")
     return y
@@ -177,6 +233,7 @@ def timestep_embedding(t, freqs):
     _require_cuda(t, freqs)
     assert t.dtype == torch.int64 and freqs.dtype == torch.float32
     out = torch.empty((t.shape[0], 2 * freqs.shape[0]), device=t.device, dtype=torch.float32)
+    _count(1)
     check(_lib.load().ctrlora_timestep_embedding(_dp(t), _dp(freqs), _dp(out), t.shape[0], freqs.shape[0], _sp()),
           "timestep_embedding")
     return out
@@ -190,6 +247,7 @@ def small_linear(x, w, bias, silu_in=False, silu_out=False, out=None):
     n = w.shape[0]
     if out is None:
         out = torch.empty((rows, n), device=x.device, dtype=torch.float32)
+    _count(1)
     check(_lib.load().ctrlora_small_linear(_dp(x), x.stride(0), _dp(w), _dp(bias), _dp(out), out.stride(0), rows, n, k,
                                            int(silu_in), int(silu_out), _sp()), "small_linear")
     return out
@@ -200,6 +258,7 @@ def upsample2x(x):
     assert x.is_contiguous() and x.dtype == torch.float16
     b, h, w, c = x.shape
     y = torch.empty((b, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_upsample2x_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "upsample2x")
     return y
 
@@ -209,6 +268,7 @@ def im2col_s2(x):
     assert x.is_contiguous() and x.dtype == torch.float16
     b, h, w, c = x.shape
     y = torch.empty((b, h // 2, w // 2, 9 * c), device=x.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_im2col_s2_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "im2col_s2")
     return y
 
@@ -219,6 +279,7 @@ def cast_transpose(src, batch, rows, cols, out=None):
     assert src.dtype == torch.float32 and src.is_contiguous() and src.numel() == batch * rows * cols
     if out is None:
         out = torch.empty((batch, cols, rows), device=src.device, dtype=torch.float16)
+    _count(1)
     check(_lib.load().ctrlora_cast_transpose_f32_to_f16(_dp(src), _dp(out), batch, rows, cols, _sp()), "cast_transpose")
     return out
 
@@ -231,6 +292,7 @@ def ddim_update(x, e_cond, e_uncond, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_m
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape)
     x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
     b = x.shape[0]
+    _count(1)
     check(_lib.load().ctrlora_ddim_update(_dp(x), _dp(e_cond), _dp(e_uncond), _dp(noise), _dp(x_prev), _dp(pred_x0),
                                           _dp(stats), b, x[0].numel(), float(cfg_scale), float(a_t), float(a_prev),
                                           float(sigma_t), float(sqrt_one_minus_at), float(temperature), _sp()),
