@@ -208,10 +208,10 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    from ctrlora_b200 import ops
-    from cldm.ddim_hacked import DDIMSampler  # noqa: E402  (dropin activated in build_model)
+    from ctrlora_b200 import dropin, ops
+    dropin.activate()
+    from cldm.ddim_hacked import DDIMSampler
     model = build_model(device, seed=rank)
-    from cldm.ddim_hacked import DDIMSampler  # noqa: F811
     sampler = DDIMSampler(model, batched_cfg=True, use_cuda_graph=True)
     sampler.make_schedule(50, ddim_eta=0.0, verbose=False)
     S = len(sampler.ddim_timesteps)
