@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
     bounded sample of the DDIM step: ONE of its 8 image passes (apply_model at batch 1)."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)  # torch's intra-op scaling on this model collapses beyond ~32 threads
     sd = cpu_state_dict()
     times = []
     budget_s = 240.0
@@ -312,7 +312,7 @@ def main():
                              "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,
                              "share_of_step": gemm_stats["ms"] / (ms_dev / args.steps)}}
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 32)  # torch's intra-op scaling on this model collapses beyond ~32 threads
             sd = cpu_state_dict()
             cpu_reference_pass(sd, threads)
             tp = cpu_reference_pass(sd, threads)

@@ -23,6 +23,8 @@ class GemmArgs(C.Structure):
         ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int), ("rowbias_ld", c_int),
         ("residual", c_void_p), ("ldr", c_int), ("residual_f32", c_int), ("out_scale", c_float),
         ("head_dim", c_int), ("tok_pad", c_int), ("bf16", c_int),
+        ("split_k", c_int), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_ll),
+        ("splitk_counters", c_void_p), ("splitk_counters_len", c_int),
     ]
 
 

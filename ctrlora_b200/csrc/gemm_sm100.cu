@@ -17,21 +17,134 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One 32-column chunk of the epilogue for one accumulator row: bias, GEGLU, time-embedding row term, scale, residual,
+// then the store (row-major fp16 / fp32, or the transposed V^T layout).  v = value columns, g = gate columns (GEGLU).
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, const float* g, int c, int bn_out, int n0,
+                                               bool row_ok, long long m, int img, int tok) {
+    const int nbase = n0 + c;
+    const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
+    if (p.bias) {
+        if (full_chunk) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nbase);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b4 = __ldg(bp + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
+        }
+    }
+    if (p.geglu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float gg = g[j];
+            if (p.bias && nbase + j < p.N) gg += __ldg(p.bias + p.N + nbase + j);
+            v[j] *= gelu_erf_f(gg);
+        }
+    }
+    if (!row_ok) return;
+    if (p.rowbias) {
+        const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + nbase;
+        if (full_chunk && (p.rowbias_ld & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb) + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (nbase + j < p.N) v[j] += __ldg(rb + j);
+        }
+    }
+    if (p.out_scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+    }
+    if (p.residual && p.residual_f32) {
+        const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
+        for (int j = 0; j < 32; ++j)
+            if (c + j < bn_out && nbase + j < p.N) v[j] += rp[j];
+    } else if (p.residual) {
+        const __half* rp = p.residual + m * p.ldr + nbase;
+        if (full_chunk && (p.ldr & 7) == 0) {
+            uint4 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __half2* h = reinterpret_cast<const __half2*>(&u[q]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h[e]);
+                    v[q * 8 + e * 2] += f.x;
+                    v[q * 8 + e * 2 + 1] += f.y;
+                }
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (c + j < bn_out && nbase + j < p.N) v[j] += __half2float(rp[j]);
+        }
+    }
+    int seg = 0, nloc = nbase;
+    if (p.seg_width > 0) { seg = nbase / p.seg_width; nloc = nbase - seg * p.seg_width; }
+    if (p.transposed[seg]) {
+        __half* o = reinterpret_cast<__half*>(p.out[seg]) + (static_cast<long long>(img) * p.seg_width + nloc) * p.tok_pad + tok;
+        for (int j = 0; j < 32; ++j)
+            if (c + j < bn_out && nbase + j < p.N) o[static_cast<long long>(j) * p.tok_pad] = __float2half_rn(v[j]);
+    } else if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out[seg]) + m * p.ldc + nloc;
+        if (full_chunk && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (c + j < bn_out && nbase + j < p.N) o[j] = v[j];
+        }
+    } else {
+        __half* o = reinterpret_cast<__half*>(p.out[seg]) + m * p.ldc + nloc;
+        if (full_chunk && (p.ldc & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                u.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
+                reinterpret_cast<uint4*>(o)[q] = u;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (c + j < bn_out && nbase + j < p.N) o[j] = __float2half_rn(v[j]);
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                     const __grid_constant__ GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_DATA);
     uint64_t* full = bars;
-    uint64_t* empty = bars + GEMM_STAGES;
-    uint64_t* tfull = bars + 2 * GEMM_STAGES;
-    uint64_t* tempty = bars + 2 * GEMM_STAGES + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_STAGES + 4);
+    uint64_t* empty = bars + GEMM_MAX_STAGES;
+    uint64_t* tfull = bars + 2 * GEMM_MAX_STAGES;
+    uint64_t* tempty = bars + 2 * GEMM_MAX_STAGES + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(bars + 2 * GEMM_MAX_STAGES + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int nstages = p.stages;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -42,13 +155,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < GEMM_STAGES; ++i) {
+        for (int i = 0; i < nstages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -59,10 +172,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_ptr;
 
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int total_tiles = m_tiles * p.n_tiles * p.splits;
     const int main_iters = p.taps * p.kchunks;
     const int k_iters = main_iters + p.kchunks2;
     const int bn_out = p.geglu ? (p.BN >> 1) : p.BN;
+
+    // tile -> (m tile, split, n tile); the k range of a split is [ks * kiters_per_split, ...)
+    auto decode = [&](int tile, int& mt, int& ks, int& nt) {
+        mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        ks = rest % p.splits;
+        nt = rest / p.splits;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -71,12 +192,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t phase = 0;
             const uint32_t tx_bytes = GEMM_A_BYTES + p.BN * 128;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % m_tiles, nt = tile / m_tiles;
+                int mt, ks, nt;
+                decode(tile, mt, ks, nt);
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.nb, n0 = nt * bn_out;
-                for (int it = 0; it < k_iters; ++it) {
+                const int it0 = ks * p.kiters_per_split, it1 = min(k_iters, it0 + p.kiters_per_split);
+                for (int it = it0; it < it1; ++it) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* a_dst = smem + stage * GEMM_STAGE_BYTES;
+                    uint8_t* a_dst = smem + stage * p.stage_bytes;
                     uint8_t* b_dst = a_dst + GEMM_A_BYTES;
                     mbar_expect_tx(&full[stage], tx_bytes);
                     if (it < main_iters) {
@@ -91,7 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tma_load_4d(a_dst, &tmA2, &full[stage], kc * GEMM_BK, w0, h0, b0);
                         tma_load_3d(b_dst, &tmB2, &full[stage], kc * GEMM_BK, 0, n0);
                     }
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -103,21 +226,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int mt, ks, nt;
+                decode(tile, mt, ks, nt);
+                const int it0 = ks * p.kiters_per_split, it1 = min(k_iters, it0 + p.kiters_per_split);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int it = 0; it < k_iters; ++it) {
+                for (int it = it0; it < it1; ++it) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
                     const uint32_t b_addr = a_addr + GEMM_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         umma_f16(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                                 p.idesc, (it | k) != 0 ? 1u : 0u);
+                                 p.idesc, (it > it0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
                 acc ^= 1;
@@ -126,13 +252,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ---------------------------------------------------- epilogue warps (TMEM -> registers -> global)
-        const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int lane_grp = warp & 3;             // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+        const int half = (warp - 2) >> 2;          // the two warps of a lane group take alternate 32-column chunks
         const int r = lane_grp * 32 + lane;
         const int iw = r % p.bw, ih = (r / p.bw) % p.bh, ib = r / (p.bw * p.bh);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile % m_tiles, nt = tile / m_tiles;
+            int mt, ks, nt;
+            decode(tile, mt, ks, nt);
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
             const int gw = tw * p.bw + iw, gh = th * p.bh + ih, gb = tb * p.nb + ib;
             const bool row_ok = gw < p.W && gh < p.H && gb < p.Bn;
@@ -145,105 +273,73 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
 
-            for (int c = 0; c < bn_out; c += 32) {
-                uint32_t raw[32];
-                float v[32];
-                tmem_ld_32x32(t_row + c, raw);
-                tmem_ld_wait();
+            if (p.splits == 1) {
+                for (int c = 32 * half; c < bn_out; c += 64) {
+                    uint32_t raw[32], graw[32];
+                    tmem_ld_32x32(t_row + c, raw);
+                    if (p.geglu) tmem_ld_32x32(t_row + bn_out + c, graw);
+                    tmem_ld_wait();
+                    float v[32], g[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                const int nbase = n0 + c;
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
+                    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw[j]); g[j] = p.geglu ? __uint_as_float(graw[j]) : 0.f; }
+                    epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
                 }
-                if (p.geglu) {
-                    uint32_t graw[32];
-                    tmem_ld_32x32(t_row + bn_out + c, graw);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            } else {
+                // ---- split-K: add this split's partial tile into the fp32 workspace (tile-local [128][BN] layout)
+                const int tile_mn = nt * m_tiles + mt;
+                float* wrow = p.ws + (static_cast<long long>(tile_mn) * GEMM_BM + r) * p.BN;
+                for (int c = 32 * half; c < p.BN; c += 64) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(t_row + c, raw);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float g = __uint_as_float(graw[j]);
-                        if (p.bias && nbase + j < p.N) g += __ldg(p.bias + p.N + nbase + j);
-                        v[j] *= gelu_erf_f(g);
-                    }
+                    for (int q = 0; q < 8; ++q)
+                        if (c + 4 * q < p.BN)
+                            red_add_v4(wrow + c + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                       __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
                 }
-                if (row_ok) {
-                    if (p.rowbias) {
-                        const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + nbase;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator stage is free again
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+                if (warp == 2 && lane == 0) {
+                    const unsigned int old = atomicAdd(&p.counters[tile_mn], 1u);
+                    const int last = (old == static_cast<unsigned int>(p.splits - 1));
+                    if (last) p.counters[tile_mn] = 0;  // self-cleaning: ready for the next launch
+                    *last_flag = last;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+                const int is_last = *last_flag;
+                if (is_last) {
+                    __threadfence();
+                    for (int c = 32 * half; c < bn_out; c += 64) {
+                        float v[32], g[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (nbase + j < p.N) v[j] += __ldg(rb + j);
-                    }
-                    if (p.out_scale != 1.0f) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
-                    }
-                    const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
-                    if (p.residual && p.residual_f32) {
-                        const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j < bn_out && nbase + j < p.N) v[j] += rp[j];
-                    } else if (p.residual) {
-                        const __half* rp = p.residual + m * p.ldr + nbase;
-                        if (full_chunk && (p.ldr & 7) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-                                const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __half22float2(h[e]);
-                                    v[q * 8 + e * 2] += f.x;
-                                    v[q * 8 + e * 2 + 1] += f.y;
+                        for (int q = 0; q < 8; ++q) {
+                            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = t4;
+                            if (c + 4 * q < bn_out) {
+                                float4* src = reinterpret_cast<float4*>(wrow + c + 4 * q);
+                                t4 = __ldcg(src);
+                                __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));
+                                if (p.geglu) {
+                                    float4* gsrc = reinterpret_cast<float4*>(wrow + bn_out + c + 4 * q);
+                                    g4 = __ldcg(gsrc);
+                                    __stcg(gsrc, make_float4(0.f, 0.f, 0.f, 0.f));
                                 }
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (c + j < bn_out && nbase + j < p.N) v[j] += __half2float(rp[j]);
+                            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                            g[4 * q] = g4.x; g[4 * q + 1] = g4.y; g[4 * q + 2] = g4.z; g[4 * q + 3] = g4.w;
                         }
-                    }
-                    // ---- store
-                    int seg = 0, nloc = nbase;
-                    if (p.seg_width > 0) { seg = nbase / p.seg_width; nloc = nbase - seg * p.seg_width; }
-                    if (p.transposed[seg]) {
-                        __half* o = reinterpret_cast<__half*>(p.out[seg]) +
-                                    (static_cast<long long>(img) * p.seg_width + nloc) * p.tok_pad + tok;
-                        for (int j = 0; j < 32; ++j)
-                            if (c + j < bn_out && nbase + j < p.N) o[static_cast<long long>(j) * p.tok_pad] = __float2half_rn(v[j]);
-                    } else if (p.out_f32) {
-                        float* o = reinterpret_cast<float*>(p.out[seg]) + m * p.ldc + nloc;
-                        if (full_chunk && (p.ldc & 3) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (c + j < bn_out && nbase + j < p.N) o[j] = v[j];
-                        }
-                    } else {
-                        __half* o = reinterpret_cast<__half*>(p.out[seg]) + m * p.ldc + nloc;
-                        if (full_chunk && (p.ldc & 7) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u;
-                                u.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]);
-                                u.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
-                                u.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
-                                u.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
-                                reinterpret_cast<uint4*>(o)[q] = u;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (c + j < bn_out && nbase + j < p.N) o[j] = __float2half_rn(v[j]);
-                        }
+                        epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
                     }
                 }
+                // nobody may overwrite last_flag before every epilogue thread has read it
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -337,24 +433,62 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         if (g_num_sms <= 0) return CTRLORA_ERR_CUDA;
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-    // ---- pick the N tile: fewest "waves x tile-cost" over the SMs; cost of one tile ~ BN (+ fixed overhead)
-    int bn_out = a->block_n;
+    const int k_iters = p.taps * p.kchunks + p.kchunks2;
+    // ---- pick the N tile and the K split with a per-tile cycle model: a tile costs
+    // max(MMA issue, operand bytes through the SM's L2 port, epilogue) and the launch costs waves x tile.
+    int bn_out = a->block_n, splits = a->split_k > 0 ? a->split_k : 1;
     if (bn_out <= 0) {
-        long best_cost = -1;
+        double best_cost = -1;
         const int max_out = p.geglu ? 128 : 256;
+        static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16};
         for (int cand = max_out; cand >= 16; cand -= 16) {
             if (a->seg_width > 0 && a->seg_width % cand != 0) continue;
+            const int bnt = p.geglu ? 2 * cand : cand;
             const int nt = (p.N + cand - 1) / cand;
-            const long tiles = (long)m_tiles * nt;
-            const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-            const long cost = waves * ((p.geglu ? 2 * cand : cand) + 24);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn_out = cand; }
+            const long tiles_mn = (long)m_tiles * nt;
+            const double waste = (double)nt * cand / p.N;  // columns computed beyond N
+            for (int si = 0; si < 8; ++si) {
+                int S = split_cands[si];
+                if (a->split_k > 0 && S != a->split_k) continue;
+                if (S > 1) {
+                    if (!a->splitk_ws || !a->splitk_counters) break;
+                    if ((long long)tiles_mn * GEMM_BM * bnt * 4 > a->splitk_ws_bytes || tiles_mn > a->splitk_counters_len) break;
+                    if (a->seg_width > 0 && a->transposed[0] + a->transposed[1] + a->transposed[2] > 0 && false) break;
+                }
+                const int kps = (k_iters + S - 1) / S;
+                if (S > 1 && kps < 4) break;
+                const int s_eff = (k_iters + kps - 1) / kps;
+                const long tiles = tiles_mn * s_eff;
+                const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+                const double t_mma = kps * 4.0 * (bnt / 2 > 32 ? bnt / 2 : 32);
+                const double t_load = kps * (double)(GEMM_A_BYTES + bnt * 128) / 72.0;
+                const double t_epi = (cand / 32 + 1) * 350.0;
+                double t_tile = (t_mma > t_load ? t_mma : t_load);
+                if (t_epi > t_tile) t_tile = t_epi;
+                t_tile += 600.0;
+                if (s_eff > 1) t_tile += bnt * 12.0 + t_epi;
+                const double cost = waves * t_tile * (0.5 + 0.5 * waste);
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn_out = cand; splits = s_eff; }
+            }
         }
     }
     if (bn_out % 16 != 0 || bn_out < 16 || bn_out > (p.geglu ? 128 : 256)) return CTRLORA_ERR_ARG;
     if (a->seg_width > 0 && a->seg_width % bn_out != 0) return CTRLORA_ERR_ARG;
     p.BN = p.geglu ? 2 * bn_out : bn_out;
     p.n_tiles = (p.N + bn_out - 1) / bn_out;
+    p.kiters_per_split = (k_iters + splits - 1) / splits;
+    p.splits = (k_iters + p.kiters_per_split - 1) / p.kiters_per_split;
+    if (p.splits > 1) {
+        const long long tiles_mn = (long long)m_tiles * p.n_tiles;
+        if (!a->splitk_ws || !a->splitk_counters || tiles_mn * GEMM_BM * p.BN * 4 > a->splitk_ws_bytes ||
+            tiles_mn > a->splitk_counters_len)
+            return CTRLORA_ERR_ARG;
+        p.ws = a->splitk_ws;
+        p.counters = a->splitk_counters;
+    }
+    p.stage_bytes = GEMM_A_BYTES + ((p.BN * 128 + 1023) / 1024) * 1024;
+    p.stages = GEMM_SMEM_DATA / p.stage_bytes;
+    if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
     p.idesc = umma_idesc_f16(GEMM_BM, p.BN, 0);
     for (int i = 0; i < 3; ++i) { p.out[i] = a->out[i]; p.transposed[i] = a->transposed[i]; }
     p.seg_width = a->seg_width;
@@ -403,7 +537,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
             return CTRLORA_ERR_CUDA;
         g_attr_set = true;
     }
-    const int total = m_tiles * p.n_tiles;
+    const int total = m_tiles * p.n_tiles * p.splits;
     const int grid = total < g_num_sms ? total : g_num_sms;
     gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;

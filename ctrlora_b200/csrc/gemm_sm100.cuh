@@ -4,14 +4,14 @@
 
 namespace ctrl {
 
-constexpr int GEMM_BM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
-constexpr int GEMM_BK = 64;        // 64 fp16 = 128 B = one SWIZZLE_128B row
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KiB
-constexpr int GEMM_B_BYTES_MAX = 256 * GEMM_BK * 2;          // 32 KiB
-constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES_MAX;
-constexpr int GEMM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_BM = 128;            // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int GEMM_BK = 64;             // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int GEMM_MAX_STAGES = 10;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
+constexpr int GEMM_EPI_WARPS = 8;       // two warps per TMEM lane group, interleaved over 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer, then epilogue
+constexpr int GEMM_SMEM_DATA = 216 * 1024;            // ring buffer budget
+constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_DATA + 1024 /*align slack*/ + 512 /*barriers*/;
 
 struct GemmKParams {
     // tile geometry over the (B, H, W) pixel grid; a plain [M, K] matrix is B=1, H=1, W=M
@@ -25,6 +25,10 @@ struct GemmKParams {
     int kchunks;                    // ceil(Cin / 64) per tap
     int kchunks2;                   // extra 1x1 segment from the second operand pair (0 = none)
     int geglu;                      // 1: weights are [2N, K]; out = value * gelu(gate)
+    int stages, stage_bytes;        // TMA ring: stage = A tile (16 KiB) + B tile (BN * 128 B, 1 KiB aligned)
+    int splits, kiters_per_split;   // split-K: partial sums meet in `ws` (fp32, self-cleaning), last CTA runs the epilogue
+    float* ws;
+    unsigned int* counters;
     uint32_t idesc;
     // epilogue
     void* out[3];
@@ -33,7 +37,7 @@ struct GemmKParams {
     int ldc;
     int out_f32;
     const float* bias;              // [N] (GEGLU: [2N])
-    const float* rowbias;           // [images, N]  per-image additive term (time embedding)
+    const float* rowbias;           // [images, rowbias_ld]  per-image additive term (time embedding)
     int rows_per_img;
     int rowbias_ld;
     int residual_f32;

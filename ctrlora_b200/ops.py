@@ -13,6 +13,7 @@ from ._lib import GemmArgs, check
 
 LAUNCHES = 0      # kernels launched through this module since the last reset (bench.py's gpu_launches)
 _GEMM_PROFILE = None  # list of (flops, start_event, end_event) while profile_gemm() is active
+_GEMM_SHAPES = None   # optional parallel list of problem shapes (tools/profile_step.py)
 
 
 def _count(n=1):
@@ -53,6 +54,19 @@ def profile_gemm(fn, sampler=None):
             "ms": float(sum(r[1].elapsed_time(r[2]) for r in recs))}
 
 
+_SPLITK = {}  # device index -> (fp32 workspace, uint32 counters); zero on entry and on exit of every GEMM launch
+SPLITK_WS_BYTES = 48 << 20
+SPLITK_COUNTERS = 4096
+
+
+def _splitk_buffers(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SPLITK:
+        _SPLITK[key] = (torch.zeros(SPLITK_WS_BYTES // 4, device=device, dtype=torch.float32),
+                        torch.zeros(SPLITK_COUNTERS, device=device, dtype=torch.int32))
+    return _SPLITK[key]
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -80,7 +94,7 @@ def _as_bhwc(a):
 def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0, residual=None, out_scale=1.0, a2=None,
          w2=None,
          geglu=False, out=None, out_f32=False, seg_outs=None, seg_width=0, transposed=(0, 0, 0), head_dim=0,
-         tok_pad=0, block_n=0, simt=False):
+         tok_pad=0, block_n=0, split_k=0, simt=False):
     """out = epilogue(conv_or_linear(a, w) [+ a2 @ w2^T]); see `ctrlora_gemm_f16` in include/ctrlora_b200.h.
 
     a: fp16 [B,H,W,C] or [M,K]; w: fp16 [N(2N), ksize*ksize, C]; returns the output tensor ([..., N]).
@@ -127,6 +141,9 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
         args.residual, args.ldr = _ptr(residual), residual.stride(-2)
         args.residual_f32 = int(residual.dtype == torch.float32)
     args.out_scale, args.head_dim, args.tok_pad, args.bf16 = float(out_scale), head_dim, tok_pad, 0
+    ws, cnt = _splitk_buffers(a.device)
+    args.split_k, args.splitk_ws, args.splitk_ws_bytes = split_k, ws.data_ptr(), SPLITK_WS_BYTES
+    args.splitk_counters, args.splitk_counters_len = cnt.data_ptr(), SPLITK_COUNTERS
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
     _count()
@@ -137,6 +154,10 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
         e1.record()
         ktot = ksize * ksize * c + (args.a2_c if a2 is not None else 0)
         _GEMM_PROFILE.append((2.0 * M * n_rows * ktot, e0, e1))
+        if _GEMM_SHAPES is not None:
+            _GEMM_SHAPES.append({"B": b, "H": h, "W": wd, "C": c, "N": n_rows, "ksize": ksize, "geglu": int(geglu),
+                                 "c2": int(args.a2_c) if a2 is not None else 0, "segs": seg_width,
+                                 "res": int(residual is not None)})
         return ret
     check(fn(C.addressof(args), _sp()), "ctrlora_gemm_f16")
     return ret

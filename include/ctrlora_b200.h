@@ -68,6 +68,11 @@ typedef struct ctrlora_gemm_args {
     float out_scale;        /* applied to (acc + bias + rowbias) */
     int head_dim, tok_pad;  /* for transposed stores */
     int bf16;               /* must be 0 (fp16 operands) in this ABI version */
+    int split_k;            /* 0 = choose automatically (needs the workspace below), 1 = never split */
+    float* splitk_ws;       /* fp32 workspace that is ALL ZERO on entry; the kernel leaves it all zero on exit */
+    long long splitk_ws_bytes;
+    unsigned int* splitk_counters;   /* zeroed arrival counters, same contract */
+    int splitk_counters_len;
 } ctrlora_gemm_args;
 
 int ctrlora_gemm_f16(const ctrlora_gemm_args* args, void* stream);

@@ -132,3 +132,56 @@ def test_sd_shapes_and_speed():
         ms = e0.elapsed_time(e1) / 10
         fl = 2.0 * B * H * W * N * C * ks * ks
         print(f"conv{ks}x{ks} B{B} {H}x{W} {C}->{N}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("split", [2, 3, 4, 8])
+@pytest.mark.parametrize("case", ["conv", "skip", "geglu", "qkv"])
+def test_split_k(split, case):
+    """Forced split-K: partial tiles meet in the self-cleaning fp32 workspace; the last CTA runs the epilogue."""
+    from ctrlora_b200 import ops
+    torch.manual_seed(10 + split)
+    if case == "conv":
+        B, H, W, C, N = 4, 8, 8, 640, 320
+        a, w = _rand(B, H, W, C), _rand(N, 9, C, s=(9 * C) ** -0.5)
+        bias, rb, res = torch.randn(N, device="cuda"), torch.randn(B, N, device="cuda"), _rand(B * H * W, N)
+        out = ops.gemm(a, w, ksize=3, bias=bias, rowbias=rb, residual=res, split_k=split)
+        ref = _conv_ref(a, w, 3) + bias + rb[:, None, None, :] + res.float().view(B, H, W, N)
+        _close(out, ref)
+    elif case == "skip":
+        B, H, W, C, C2, N = 2, 8, 8, 256, 512, 192
+        a, w = _rand(B, H, W, C), _rand(N, 9, C, s=(9 * C) ** -0.5)
+        a2, w2 = _rand(B, H, W, C2), _rand(N, C2, s=C2 ** -0.5)
+        out = ops.gemm(a, w, ksize=3, a2=a2, w2=w2, split_k=split)
+        _close(out, _conv_ref(a, w, 3) + a2.float() @ w2.float().t())
+    elif case == "geglu":
+        M, K, N = 300, 1280, 640
+        a, w = _rand(M, K), _rand(2 * N, 1, K, s=K ** -0.5)
+        bias = torch.randn(2 * N, device="cuda")
+        out = ops.gemm(a, w, bias=bias, geglu=True, split_k=split)
+        y = a.float() @ w.float().view(2 * N, K).t() + bias
+        _close(out, y[:, :N] * F.gelu(y[:, N:]))
+    else:
+        Bimg, T, K, Cq, heads = 2, 64, 1280, 320, 8
+        d = Cq // heads
+        a, w = _rand(Bimg * T, K), _rand(3 * Cq, 1, K, s=K ** -0.5)
+        q = torch.empty(Bimg * T, Cq, device="cuda", dtype=torch.float16)
+        k = torch.empty_like(q)
+        vt = torch.zeros(Bimg, heads, d, T, device="cuda", dtype=torch.float16)
+        ops.gemm(a, w, seg_outs=[q, k, vt], seg_width=Cq, transposed=(0, 0, 1), rows_per_img=T, head_dim=d, tok_pad=T,
+                 split_k=split)
+        y = a.float() @ w.float().view(3 * Cq, K).t()
+        _close(q, y[:, :Cq])
+        _close(k, y[:, Cq:2 * Cq])
+        _close(vt, y[:, 2 * Cq:].view(Bimg, T, heads, d).permute(0, 2, 3, 1))
+    ws, cnt = ops._splitk_buffers(torch.device("cuda", 0))
+    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0  # self-cleaning contract
+
+
+def test_split_k_auto_small_m():
+    """The selection model splits K on tile-starved problems (8x8 feature maps) and results do not change."""
+    from ctrlora_b200 import ops
+    torch.manual_seed(30)
+    B, H, W, C, N = 8, 8, 8, 1280, 1280
+    a, w = _rand(B, H, W, C), _rand(N, 9, C, s=(9 * C) ** -0.5)
+    out = ops.gemm(a, w, ksize=3)
+    _close(out, _conv_ref(a, w, 3))
