@@ -26,7 +26,7 @@ struct AttnParams {
     float scale_log2e;          // d^-1/2 * log2(e)
     __half* out;
     long long ldo;
-    uint32_t idesc_s, idesc_pv;
+    uint32_t idesc_s, idesc_pv, idesc_l;
 };
 
 constexpr int ATT_THREADS = 192;  // warps 0-3: softmax / epilogue (TMEM lane groups 0-3), warp 4: TMA, warp 5: MMA
@@ -45,8 +45,10 @@ struct AttnSmem {
     static constexpr int DATA_BYTES = MULTI ? (P_OFF + P_BYTES)
                                             : (Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES) + V_BYTES);
     static constexpr int V_OFF_SINGLE = Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES);
-    static constexpr int TOTAL = DATA_BYTES + 1024 + 128;
-    static constexpr int TMEM_COLS = (BKV + DPAD) <= 256 ? 256 : 512;
+    static constexpr int ONES_OFF = DATA_BYTES;               // [16 rows x 128 B] of fp16 1.0: row sums on the tensor core
+    static constexpr int BAR_OFF = DATA_BYTES + 2048;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 128;
+    static constexpr int TMEM_COLS = (BKV + DPAD + 16) <= 256 ? 256 : 512;
 };
 
 template <int DPAD, int BKV, bool MULTI>
@@ -56,7 +58,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     using L = AttnSmem<DPAD, BKV, MULTI>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint8_t* sOnes = smem + L::ONES_OFF;
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;   // [2]
     uint64_t* kv_empty = bars + 3;  // [2]
@@ -87,12 +90,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+    if (threadIdx.x < 128)  // 128 x 16 B = 2 KiB of 1.0h; every element equal, so the swizzle pattern is irrelevant
+        reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_s = tmem_base;          // [0, BKV)
     const uint32_t tmem_pv = tmem_base + BKV;   // [BKV, BKV + d16)
+    const uint32_t tmem_l = tmem_pv + DPAD;     // [BKV + DPAD, +16): row sums of P (P x ones)
     const int n_tiles = p.n_kv_tiles;
 
     if (warp == 4) {
@@ -141,6 +148,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     umma_f16(tmem_pv, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
                              ks != 0 ? 1u : 0u);
                 }
+                const uint32_t oa = smem_u32(sOnes);
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    umma_f16(tmem_l, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(oa), p.idesc_l,
+                             ks != 0 ? 1u : 0u);
+                }
                 umma_commit(pv_full);
                 if (MULTI) umma_commit(&kv_empty[stage]);
                 if (j + 1 < n_tiles) {
@@ -165,25 +179,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = min(BKV, p.Nk - j * BKV);  // columns >= kv_valid are TMA zero fill: masked out
-            // pass 1: row max
+            const bool full_tile = kv_valid == BKV;         // warp-uniform
+            // pass 1: row max (two TMEM loads in flight, 3-input max)
             float m_tile = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < BKV; c += 32) {
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_s + lane_off + c, raw);
+            for (int c = 0; c < BKV; c += 64) {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32(tmem_s + lane_off + c, ra);
+                tmem_ld_32x32(tmem_s + lane_off + c + 32, rb);
                 tmem_ld_wait();
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(raw[i]));
+                    for (int i = 0; i < 32; ++i) m_tile = max3f(m_tile, __uint_as_float(ra[i]), __uint_as_float(rb[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (c + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(ra[i]));
+                        if (c + 32 + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(rb[i]));
+                    }
+                }
             }
             const float m_new = fmaxf(m_run, m_tile);
             const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // first tile: exp2(-inf) = 0
             m_run = m_new;
             const float neg_ms = -m_new * p.scale_log2e;
             if (MULTI && j > 0) {
-                // fold the previous tile's PV (relative to the previous max), then rescale to the new max
+                // fold the previous tile's P*V and P*1 (both relative to the previous max), then rescale to the new max
                 mbar_wait(pv_full, (j - 1) & 1);
                 tc_fence_after();
+                uint32_t lraw;
+                tmem_ld_32x1(tmem_l + lane_off, lraw);
 #pragma unroll
                 for (int c = 0; c < DPAD; c += 16) {
                     uint32_t raw[16];
@@ -192,24 +217,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 16; ++i) o_reg[c + i] = (o_reg[c + i] + __uint_as_float(raw[i])) * alpha;
                 }
+                l_run = (l_run + __uint_as_float(lraw)) * alpha;
             }
-            // pass 2: P = exp2(s * scale*log2e - m * scale*log2e) -> fp16, swizzled K-major rows of 128 B
-            float l_tile = 0.f;
+            // pass 2: P = exp2(s * scale*log2e - m * scale*log2e) -> fp16, swizzled K-major rows of 128 B.
+            // The row sum is NOT accumulated here: it comes out of the tensor core as P x ones (tmem_l).
 #pragma unroll 1
             for (int c = 0; c < BKV; c += 32) {
                 uint32_t raw[32];
                 tmem_ld_32x32(tmem_s + lane_off + c, raw);
                 tmem_ld_wait();
                 uint32_t packed[16];
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2e, neg_ms)) : 0.f;
-                    float p1 = (c + i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2e, neg_ms)) : 0.f;
-                    __half2 h = __floats2half2_rn(p0, p1);
-                    // the row sum uses the fp16-rounded probabilities the PV product will actually see
-                    float2 f = __half22float2(h);
-                    l_tile += f.x + f.y;
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2e, neg_ms));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2e, neg_ms));
+                        packed[i >> 1] = pack_half2(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = (c + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), p.scale_log2e, neg_ms)) : 0.f;
+                        const float p1 = (c + i + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), p.scale_log2e, neg_ms)) : 0.f;
+                        packed[i >> 1] = pack_half2(p0, p1);
+                    }
                 }
                 uint8_t* chunk = sP + (c >> 6) * 128 * 128 + r * 128;
                 const int u0 = (c & 63) >> 3;  // first 16-byte unit of this 32-column group within the 128 B row
@@ -219,7 +250,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = val;
                 }
             }
-            l_run = l_run * alpha + l_tile;
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
@@ -227,7 +257,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         // ---- final: fold the last PV, normalise, store
         mbar_wait(pv_full, (n_tiles - 1) & 1);
         tc_fence_after();
-        const float inv_l = 1.0f / l_run;
+        uint32_t lfin;
+        tmem_ld_32x1(tmem_l + lane_off, lfin);
+        tmem_ld_wait();
+        const float inv_l = 1.0f / (l_run + __uint_as_float(lfin));
         const bool row_ok = (q0 + r) < p.Nq;
         __half* orow = p.out + (static_cast<long long>(img) * p.Nq + q0 + r) * p.ldo + head * p.d;
 #pragma unroll
@@ -304,6 +337,7 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
     p.n_kv_tiles = (nk + bkv - 1) / bkv;
     p.idesc_s = umma_idesc_f16(128, bkv, 0);
     p.idesc_pv = umma_idesc_f16(128, p.d16, 0);
+    p.idesc_l = umma_idesc_f16(128, 16, 0);
     CUtensorMap tq, tk, tv;
     {
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)nq, (uint64_t)batch};

@@ -449,14 +449,14 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
             const double waste = (double)nt * cand / p.N;  // columns computed beyond N
             for (int si = 0; si < 8; ++si) {
                 int S = split_cands[si];
-                if (a->split_k > 0 && S != a->split_k) continue;
+                if (a->split_k > 0) { if (si > 0) break; S = a->split_k; }
                 if (S > 1) {
                     if (!a->splitk_ws || !a->splitk_counters) break;
                     if ((long long)tiles_mn * GEMM_BM * bnt * 4 > a->splitk_ws_bytes || tiles_mn > a->splitk_counters_len) break;
                     if (a->seg_width > 0 && a->transposed[0] + a->transposed[1] + a->transposed[2] > 0 && false) break;
                 }
                 const int kps = (k_iters + S - 1) / S;
-                if (S > 1 && kps < 4) break;
+                if (S > 1 && kps < 4 && a->split_k <= 0) break;
                 const int s_eff = (k_iters + kps - 1) / kps;
                 const long tiles = tiles_mn * s_eff;
                 const long waves = (tiles + g_num_sms - 1) / g_num_sms;
