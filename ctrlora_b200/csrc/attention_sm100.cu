@@ -45,8 +45,10 @@ struct AttnSmem {
     static constexpr int DATA_BYTES = MULTI ? (P_OFF + P_BYTES)
                                             : (Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES) + V_BYTES);
     static constexpr int V_OFF_SINGLE = Q_BYTES + (K_BYTES > P_BYTES ? K_BYTES : P_BYTES);
-    static constexpr int ONES_OFF = DATA_BYTES;               // [16 rows x 128 B] of fp16 1.0: row sums on the tensor core
-    static constexpr int BAR_OFF = DATA_BYTES + 2048;
+    // [16 rows x 128 B] of fp16 1.0 (row sums on the tensor core).  Single-tile mode: aliases the Q buffer, which is
+    // dead once S = Q K^T has completed (written by the softmax warps after s_full).
+    static constexpr int ONES_OFF = MULTI ? DATA_BYTES : 0;
+    static constexpr int BAR_OFF = MULTI ? DATA_BYTES + 2048 : DATA_BYTES;
     static constexpr int TOTAL = BAR_OFF + 1024 + 128;
     static constexpr int TMEM_COLS = (BKV + DPAD + 16) <= 256 ? 256 : 512;
 };
@@ -90,7 +92,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
-    if (threadIdx.x < 128)  // 128 x 16 B = 2 KiB of 1.0h; every element equal, so the swizzle pattern is irrelevant
+    if (MULTI && threadIdx.x < 128)  // 128 x 16 B = 2 KiB of 1.0h; all elements equal, so the swizzle is irrelevant
         reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -178,6 +180,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
+            if (!MULTI)  // Q is dead now: its first 2 KiB become the ones tile (made visible by the fence before p_full)
+                reinterpret_cast<uint4*>(sOnes)[r] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
             const int kv_valid = min(BKV, p.Nk - j * BKV);  // columns >= kv_valid are TMA zero fill: masked out
             const bool full_tile = kv_valid == BKV;         // warp-uniform
             // pass 1: row max (two TMEM loads in flight, 3-input max)

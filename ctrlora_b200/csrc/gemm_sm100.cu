@@ -451,6 +451,8 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
                 int S = split_cands[si];
                 if (a->split_k > 0) { if (si > 0) break; S = a->split_k; }
                 if (S > 1) {
+                    if (a->split_k <= 0) break;  // measured (tools/sweep_gemm.py): the atomic-add reduction costs more than
+                                                 // it saves at every shape of the 512x512 path; only an explicit request splits
                     if (!a->splitk_ws || !a->splitk_counters) break;
                     if ((long long)tiles_mn * GEMM_BM * bnt * 4 > a->splitk_ws_bytes || tiles_mn > a->splitk_counters_len) break;
                     if (a->seg_width > 0 && a->transposed[0] + a->transposed[1] + a->transposed[2] > 0 && false) break;

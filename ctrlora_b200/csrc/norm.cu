@@ -51,7 +51,19 @@ gn_stats_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __
         float a[8], q[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { a[e] = 0.f; q[e] = 0.f; }
-        for (int p = p0 + pl; p < p1; p += lanes) {
+        // four independent 16 B loads in flight per thread: this kernel is pure latency/bandwidth
+        int p = p0 + pl;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8(s, static_cast<long long>(b) * HW + p + u * lanes, vec * 8, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { a[e] += v[u][e]; q[e] += v[u][e] * v[u][e]; }
+            }
+        }
+        for (; p < p1; p += lanes) {
             float v[8];
             load8(s, static_cast<long long>(b) * HW + p, vec * 8, v);
 #pragma unroll
@@ -94,10 +106,7 @@ gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const flo
     }
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(HW, p0 + pix_per_block);
-    for (int p = p0 + pl; p < p1; p += lanes) {
-        const long long pix = static_cast<long long>(b) * HW + p;
-        float v[8];
-        load8(s, pix, vec * 8, v);
+    auto emit = [&](long long pix, float* v) {
         if (raw) {
             uint4 u;
             __half2* h = reinterpret_cast<__half2*>(&u);
@@ -107,7 +116,7 @@ gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const flo
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float t = v[e] * sc[e] + sh[e];
+            const float t = v[e] * sc[e] + sh[e];
             v[e] = silu ? silu_f(t) : t;
         }
         uint4 u;
@@ -115,6 +124,19 @@ gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const flo
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
         *reinterpret_cast<uint4*>(y + pix * C + vec * 8) = u;
+    };
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(s, static_cast<long long>(b) * HW + p + u * lanes, vec * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) emit(static_cast<long long>(b) * HW + p + u * lanes, v[u]);
+    }
+    for (; p < p1; p += lanes) {
+        float v[8];
+        load8(s, static_cast<long long>(b) * HW + p, vec * 8, v);
+        emit(static_cast<long long>(b) * HW + p, v);
     }
 }
 
