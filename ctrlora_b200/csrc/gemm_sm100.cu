@@ -288,9 +288,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
             } else {
-                // ---- split-K: add this split's partial tile into the fp32 workspace (tile-local [128][BN] layout)
+                // ---- split-K: park this split's partial tile in its own fp32 workspace slice (plain stores)
                 const int tile_mn = nt * m_tiles + mt;
-                float* wrow = p.ws + (static_cast<long long>(tile_mn) * GEMM_BM + r) * p.BN;
+                const long long slice = static_cast<long long>(GEMM_BM) * p.BN;
+                float* wrow0 = p.ws + static_cast<long long>(tile_mn) * p.splits * slice + static_cast<long long>(r) * p.BN;
+                float* wrow = wrow0 + ks * slice;
                 for (int c = 32 * half; c < p.BN; c += 64) {
                     uint32_t raw[32];
                     tmem_ld_32x32(t_row + c, raw);
@@ -298,8 +300,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if (c + 4 * q < p.BN)
-                            red_add_v4(wrow + c + 4 * q, __uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
-                                       __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+                            __stcg(reinterpret_cast<float4*>(wrow + c + 4 * q),
+                                   make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                               __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -322,13 +325,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int q = 0; q < 8; ++q) {
                             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = t4;
                             if (c + 4 * q < bn_out) {
-                                float4* src = reinterpret_cast<float4*>(wrow + c + 4 * q);
-                                t4 = __ldcg(src);
-                                __stcg(src, make_float4(0.f, 0.f, 0.f, 0.f));
-                                if (p.geglu) {
-                                    float4* gsrc = reinterpret_cast<float4*>(wrow + bn_out + c + 4 * q);
-                                    g4 = __ldcg(gsrc);
-                                    __stcg(gsrc, make_float4(0.f, 0.f, 0.f, 0.f));
+                                for (int sl = 0; sl < p.splits; ++sl) {  // fixed order: deterministic sums
+                                    const float4 x4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + c + 4 * q));
+                                    t4.x += x4.x; t4.y += x4.y; t4.z += x4.z; t4.w += x4.w;
+                                    if (p.geglu) {
+                                        const float4 y4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + bn_out + c + 4 * q));
+                                        g4.x += y4.x; g4.y += y4.y; g4.z += y4.z; g4.w += y4.w;
+                                    }
                                 }
                             }
                             v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
@@ -454,7 +457,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
                     if (a->split_k <= 0) break;  // measured (tools/sweep_gemm.py): the atomic-add reduction costs more than
                                                  // it saves at every shape of the 512x512 path; only an explicit request splits
                     if (!a->splitk_ws || !a->splitk_counters) break;
-                    if ((long long)tiles_mn * GEMM_BM * bnt * 4 > a->splitk_ws_bytes || tiles_mn > a->splitk_counters_len) break;
+                    if ((long long)tiles_mn * S * GEMM_BM * bnt * 4 > a->splitk_ws_bytes || tiles_mn > a->splitk_counters_len) break;
                     if (a->seg_width > 0 && a->transposed[0] + a->transposed[1] + a->transposed[2] > 0 && false) break;
                 }
                 const int kps = (k_iters + S - 1) / S;
@@ -482,7 +485,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     p.splits = (k_iters + p.kiters_per_split - 1) / p.kiters_per_split;
     if (p.splits > 1) {
         const long long tiles_mn = (long long)m_tiles * p.n_tiles;
-        if (!a->splitk_ws || !a->splitk_counters || tiles_mn * GEMM_BM * p.BN * 4 > a->splitk_ws_bytes ||
+        if (!a->splitk_ws || !a->splitk_counters || tiles_mn * p.splits * GEMM_BM * p.BN * 4 > a->splitk_ws_bytes ||
             tiles_mn > a->splitk_counters_len)
             return CTRLORA_ERR_ARG;
         p.ws = a->splitk_ws;

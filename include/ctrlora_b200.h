@@ -69,9 +69,9 @@ typedef struct ctrlora_gemm_args {
     int head_dim, tok_pad;  /* for transposed stores */
     int bf16;               /* must be 0 (fp16 operands) in this ABI version */
     int split_k;            /* 0 = choose automatically (needs the workspace below), 1 = never split */
-    float* splitk_ws;       /* fp32 workspace that is ALL ZERO on entry; the kernel leaves it all zero on exit */
+    float* splitk_ws;       /* fp32 scratch for the per-split partial tiles (no initial contents required) */
     long long splitk_ws_bytes;
-    unsigned int* splitk_counters;   /* zeroed arrival counters, same contract */
+    unsigned int* splitk_counters;   /* arrival counters: all zero on entry, left all zero on exit */
     int splitk_counters_len;
 } ctrlora_gemm_args;
 

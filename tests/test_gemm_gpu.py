@@ -137,7 +137,8 @@ def test_sd_shapes_and_speed():
 @pytest.mark.parametrize("split", [2, 3, 4, 8])
 @pytest.mark.parametrize("case", ["conv", "skip", "geglu", "qkv"])
 def test_split_k(split, case):
-    """Forced split-K: partial tiles meet in the self-cleaning fp32 workspace; the last CTA runs the epilogue."""
+    """Forced split-K: partial tiles are parked in fp32 workspace slices; the last CTA to arrive sums them (fixed order)
+    and runs the epilogue."""
     from ctrlora_b200 import ops
     torch.manual_seed(10 + split)
     if case == "conv":
@@ -174,7 +175,7 @@ def test_split_k(split, case):
         _close(k, y[:, Cq:2 * Cq])
         _close(vt, y[:, 2 * Cq:].view(Bimg, T, heads, d).permute(0, 2, 3, 1))
     ws, cnt = ops._splitk_buffers(torch.device("cuda", 0))
-    assert ws.abs().max().item() == 0 and cnt.abs().max().item() == 0  # self-cleaning contract
+    assert cnt.abs().max().item() == 0  # counters are self-cleaning
 
 
 def test_split_k_auto_small_m():
