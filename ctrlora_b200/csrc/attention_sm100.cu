@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (MULTI && DPAD <= 48) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
     using L = AttnSmem<DPAD, BKV, MULTI>;
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -99,6 +100,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
     const uint32_t tmem_s = tmem_base;          // [0, BKV)
     const uint32_t tmem_pv = tmem_base + BKV;   // [BKV, BKV + d16)
     const uint32_t tmem_l = tmem_pv + DPAD;     // [BKV + DPAD, +16): row sums of P (P x ones)
@@ -314,7 +316,9 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
             return CTRLORA_ERR_CUDA;
         attr = true;
     }
-    attention_kernel<DPAD, BKV, MULTI><<<grid, ATT_THREADS, L::TOTAL, stream>>>(tq, tk, tv, p);
+    if (launch_pdl(attention_kernel<DPAD, BKV, MULTI>, grid, dim3(ATT_THREADS), (size_t)L::TOTAL, stream, tq, tk, tv, p) !=
+        cudaSuccess)
+        return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
 

@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define CTRLORA_OK 0
 #define CTRLORA_ERR_ARG 1
@@ -167,6 +169,35 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
 __device__ __host__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int fmt) {
     return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
            (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every hot kernel starts with launch_dependents (the next kernel in the stream may begin its prologue: barrier init,
+// TMEM allocation, descriptor prefetch) and executes wait before its first global-memory access.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              KArgs... args) {
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("CTRLORA_PDL");
+        use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    void* ptrs[] = {(void*)&args...};
+    return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), ptrs);
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -20,7 +20,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // One 32-column chunk of the epilogue for one accumulator row: bias, GEGLU, time-embedding row term, scale, residual,
 // then the store (row-major fp16 / fp32, or the transposed V^T layout).  v = value columns, g = gate columns (GEGLU).
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, const float* g, int c, int bn_out, int n0,
-                                               bool row_ok, long long m, int img, int tok) {
+                                               bool row_ok, long long m, int img, int tok, const uint4* rpre = nullptr) {
     const int nbase = n0 + c;
     const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
     if (p.bias) {
@@ -73,7 +73,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, c
         if (full_chunk && (p.ldr & 7) == 0) {
             uint4 u[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+            for (int q = 0; q < 4; ++q) u[q] = rpre ? rpre[q] : __ldg(reinterpret_cast<const uint4*>(rp) + q);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const __half2* h = reinterpret_cast<const __half2*>(&u[q]);
@@ -142,6 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4);
     volatile int* last_flag = reinterpret_cast<volatile int*>(bars + 2 * GEMM_MAX_STAGES + 5);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nstages = p.stages;
@@ -170,6 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();  // everything above overlapped the previous kernel's tail; operands are read only from here on
 
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int total_tiles = m_tiles * p.n_tiles * p.splits;
@@ -269,20 +271,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int img = row_ok ? static_cast<int>(m / p.rows_per_img) : 0;
             const int tok = row_ok ? static_cast<int>(m % p.rows_per_img) : 0;
 
+            // pull this row's residual segment towards L2 while the tile's MMAs are still running
+            if (p.residual && row_ok && half == 0) {
+                const int esz = p.residual_f32 ? 4 : 2;
+                const char* rrow = reinterpret_cast<const char*>(p.residual) + (m * p.ldr + n0) * esz;
+                int nbytes = (min(bn_out, p.N - n0) * esz) & ~15;
+                if (nbytes > 0 && (reinterpret_cast<uintptr_t>(rrow) & 15) == 0)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rrow), "r"(nbytes) : "memory");
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
 
             if (p.splits == 1) {
+                const bool res16 = p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && row_ok;
                 for (int c = 32 * half; c < bn_out; c += 64) {
                     uint32_t raw[32], graw[32];
                     tmem_ld_32x32(t_row + c, raw);
                     if (p.geglu) tmem_ld_32x32(t_row + bn_out + c, graw);
+                    // residual loads are issued before the TMEM wait so the two latencies overlap
+                    uint4 rpre[4];
+                    const bool pre = res16 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
+                    if (pre) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rpre[q] = __ldg(rp + q);
+                    }
                     tmem_ld_wait();
                     float v[32], g[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw[j]); g[j] = p.geglu ? __uint_as_float(graw[j]) : 0.f; }
-                    epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
+                    epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok, pre ? rpre : nullptr);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -544,6 +563,8 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     }
     const int total = m_tiles * p.n_tiles * p.splits;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    if (launch_pdl(gemm_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES, stream, tmA, tmB, tmA2,
+                   tmB2, p) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }

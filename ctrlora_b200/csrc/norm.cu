@@ -36,6 +36,8 @@ __device__ __forceinline__ void load8(const GnSrc& s, long long pix, int c, floa
 // stats[b][g] = {sum, sumsq} accumulated with atomics (buffer zeroed by the launcher)
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // [2][C]
     float* csum = sm;
     float* csq = sm + C;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(512)
 gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                 __half* __restrict__ y, __half* __restrict__ raw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const int vecs = C >> 3;
     const int lanes = blockDim.x / vecs;
@@ -145,6 +149,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy, int M, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -222,11 +228,12 @@ extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stre
     const int vecs = C / 8;
     const int lanes = vecs >= 256 ? 1 : 256 / vecs;
     const int threads = vecs * lanes;  // every thread owns one 8-channel vector of one pixel lane
+    // the stats kernel follows a memset node (plain launch); the apply kernel chains onto it programmatically
     gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(s, C, HW, a->groups, ppb,
                                                                  reinterpret_cast<float*>(a->stats_ws));
-    gn_apply_kernel<<<grid, threads, 0, stream>>>(s, C, HW, a->groups, ppb, reinterpret_cast<const float*>(a->stats_ws),
-                                              a->gamma, a->beta, a->eps, a->silu, reinterpret_cast<__half*>(a->y),
-                                              reinterpret_cast<__half*>(a->raw_out));
+    launch_pdl(gn_apply_kernel, grid, dim3(threads), (size_t)0, stream, s, C, HW, (int)a->groups, ppb,
+               reinterpret_cast<const float*>(a->stats_ws), a->gamma, a->beta, a->eps, (int)a->silu,
+               reinterpret_cast<__half*>(a->y), reinterpret_cast<__half*>(a->raw_out));
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
 
@@ -237,8 +244,8 @@ extern "C" int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long
     const int grid = (rows + 7) / 8;
     const __half* xp = reinterpret_cast<const __half*>(x);
     __half* yp = reinterpret_cast<__half*>(y);
-    if (cols <= 512) layernorm_kernel<2><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
-    else if (cols <= 1280) layernorm_kernel<5><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
-    else layernorm_kernel<8><<<grid, 256, 0, stream>>>(xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    if (cols <= 512) launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), (size_t)0, stream, xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    else if (cols <= 1280) launch_pdl(layernorm_kernel<5>, dim3(grid), dim3(256), (size_t)0, stream, xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
+    else launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), (size_t)0, stream, xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
