@@ -78,6 +78,7 @@ _ARGTYPES = {
     "ctrlora_im2col_s2_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_cast_transpose_f32_to_f16": [_P, _P, _L, _I, _I, _P],
     "ctrlora_ddim_update": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P],
+    "ctrlora_wgrad_tn_f16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _F, _F, _P, _L, _P],
 }
 
 
@@ -114,4 +115,5 @@ EXPORTS = [
     "ctrlora_im2col_s2_f16",
     "ctrlora_cast_transpose_f32_to_f16",
     "ctrlora_ddim_update",
+    "ctrlora_wgrad_tn_f16",
 ]

@@ -19,6 +19,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // One 32-column chunk of the epilogue for one accumulator row: bias, GEGLU, time-embedding row term, scale, residual,
 // then the store (row-major fp16 / fp32, or the transposed V^T layout).  v = value columns, g = gate columns (GEGLU).
+template <bool GEGLU>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, const float* g, int c, int bn_out, int n0,
                                                bool row_ok, long long m, int img, int tok, const uint4* rpre = nullptr) {
     const int nbase = n0 + c;
@@ -37,7 +38,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, c
                 if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
         }
     }
-    if (p.geglu) {
+    if (GEGLU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float gg = g[j];
@@ -128,6 +129,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool GEGLU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -177,7 +179,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int total_tiles = m_tiles * p.n_tiles * p.splits;
     const int main_iters = p.taps * p.kchunks;
     const int k_iters = main_iters + p.kchunks2;
-    const int bn_out = p.geglu ? (p.BN >> 1) : p.BN;
+    const int bn_out = GEGLU ? (p.BN >> 1) : p.BN;
 
     // tile -> (m tile, split, n tile); the k range of a split is [ks * kiters_per_split, ...)
     auto decode = [&](int tile, int& mt, int& ks, int& nt) {
@@ -209,7 +211,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
                         tma_load_4d(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
                         tma_load_3d(b_dst, &tmB, &full[stage], kc * GEMM_BK, tap, n0);
-                        if (p.geglu)
+                        if (GEGLU)
                             tma_load_3d(b_dst + bn_out * 128, &tmB, &full[stage], kc * GEMM_BK, tap, p.N + n0);
                     } else {
                         const int kc = it - main_iters;
@@ -271,37 +273,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int img = row_ok ? static_cast<int>(m / p.rows_per_img) : 0;
             const int tok = row_ok ? static_cast<int>(m % p.rows_per_img) : 0;
 
-            // pull this row's residual segment towards L2 while the tile's MMAs are still running
-            if (p.residual && row_ok && half == 0) {
-                const int esz = p.residual_f32 ? 4 : 2;
-                const char* rrow = reinterpret_cast<const char*>(p.residual) + (m * p.ldr + n0) * esz;
-                int nbytes = (min(bn_out, p.N - n0) * esz) & ~15;
-                if (nbytes > 0 && (reinterpret_cast<uintptr_t>(rrow) & 15) == 0)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rrow), "r"(nbytes) : "memory");
+            // issue this tile's residual loads now: they complete while the tile's MMAs are still running
+            uint4 rres[3][4];
+            const bool res16 = !GEGLU && p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && row_ok && p.splits == 1;
+            if (res16) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int c = 32 * half + 64 * i;
+                    if (c + 32 <= bn_out && n0 + c + 32 <= p.N) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rres[i][q] = __ldg(rp + q);
+                    }
+                }
             }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
 
             if (p.splits == 1) {
-                const bool res16 = p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && row_ok;
-                for (int c = 32 * half; c < bn_out; c += 64) {
-                    uint32_t raw[32], graw[32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {  // bn_out <= 256: at most four 32-column chunks per warp
+                    const int c = 32 * half + 64 * i;
+                    if (c >= bn_out) break;
+                    uint32_t raw[32];
+                    float v[32], g[GEGLU ? 32 : 1];
                     tmem_ld_32x32(t_row + c, raw);
-                    if (p.geglu) tmem_ld_32x32(t_row + bn_out + c, graw);
-                    // residual loads are issued before the TMEM wait so the two latencies overlap
-                    uint4 rpre[4];
-                    const bool pre = res16 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
-                    if (pre) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + c);
+                    if (GEGLU) {
+                        uint32_t graw[32];
+                        tmem_ld_32x32(t_row + bn_out + c, graw);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) rpre[q] = __ldg(rp + q);
+                        for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[j]);
+                    } else {
+                        tmem_ld_wait();
                     }
-                    tmem_ld_wait();
-                    float v[32], g[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw[j]); g[j] = p.geglu ? __uint_as_float(graw[j]) : 0.f; }
-                    epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok, pre ? rpre : nullptr);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                    const bool pre = res16 && i < 3 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
+                    epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, pre ? rres[i < 3 ? i : 0] : nullptr);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -347,7 +357,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int sl = 0; sl < p.splits; ++sl) {  // fixed order: deterministic sums
                                     const float4 x4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + c + 4 * q));
                                     t4.x += x4.x; t4.y += x4.y; t4.z += x4.z; t4.w += x4.w;
-                                    if (p.geglu) {
+                                    if (GEGLU) {
                                         const float4 y4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + bn_out + c + 4 * q));
                                         g4.x += y4.x; g4.y += y4.y; g4.z += y4.z; g4.w += y4.w;
                                     }
@@ -356,7 +366,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
                             g[4 * q] = g4.x; g[4 * q + 1] = g4.y; g[4 * q + 2] = g4.z; g[4 * q + 3] = g4.w;
                         }
-                        epilogue_chunk(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
+                        epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
                     }
                 }
                 // nobody may overwrite last_flag before every epilogue thread has read it
@@ -556,15 +566,17 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         tmB2 = tmB;
     }
     if (!g_attr_set) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
             return CTRLORA_ERR_CUDA;
         g_attr_set = true;
     }
     const int total = m_tiles * p.n_tiles * p.splits;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    if (launch_pdl(gemm_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES, stream, tmA, tmB, tmA2,
-                   tmB2, p) != cudaSuccess)
-        return CTRLORA_ERR_CUDA;
+    const cudaError_t lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
+                                                 stream, tmA, tmB, tmA2, tmB2, p)
+                                    : launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
+                                                 stream, tmA, tmB, tmA2, tmB2, p);
+    if (lrc != cudaSuccess) return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }

@@ -1,0 +1,219 @@
+// Weight-gradient GEMM ("TN"): C[P, Q] = sum_m A[m, P] * B[m, Q]   (fp16 operands, fp32 result)
+// for the trainable set of the CtrLoRA finetune (reference optimizer filter cldm/cldm_ctrlora_finetune.py:88-100):
+//   LoRA   dUp   = dY^T (X Down^T),  dDown = (dY Up)^T X      (factored: no dense dW is ever formed)
+//   zero-conv dW = dY^T H            (1x1 convs, cldm/cldm.py:281-282)
+// Both operands are row-major over the token dimension m, i.e. "MN-major" for the tensor core: TMA boxes of
+// [64 tokens][64 features] (128-byte rows, SWIZZLE_128B) are consumed by tcgen05.mma with a_major = b_major = MN.
+// The token dimension is split across CTAs; every CTA parks its fp32 partial tile in a workspace slice and a second
+// kernel sums the slices in a fixed order (deterministic; no atomics).
+#include "common.cuh"
+#include "ctrlora_b200.h"
+#include "gemm_sm100.cuh"
+
+namespace ctrl {
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+constexpr int WG_BK = 64;          // tokens per pipeline stage
+constexpr int WG_STAGES = 8;        // upper bound; the launcher fits as many as 200 KiB allow
+constexpr int WG_THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int WG_A_BYTES = 2 * WG_BK * 128;  // two 64-feature atoms of the 128-row P tile
+
+struct WgradParams {
+    int P, Q, M;
+    int q_tile;        // multiple of 64, <= 256
+    int q_atoms;       // q_tile / 64
+    int p_tiles, q_tiles, splits;
+    int kiters_per_split;
+    int stage_bytes, stages;
+    uint32_t idesc;
+    float* ws;         // [splits][P_pad][Q_pad] fp32, P_pad = p_tiles*128, Q_pad = q_tiles*q_tile
+};
+
+// MN-major operand, SWIZZLE_128B: 64-feature atoms (128 B rows), 8-token groups 1024 B apart (SBO), atoms `lbo` apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ WgradParams p) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + WG_STAGES;
+    uint64_t* tfull = bars + 2 * WG_STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+
+    const int tile = blockIdx.x;
+    const int pt = tile % p.p_tiles, qt = tile / p.p_tiles;
+    const int split = blockIdx.y;
+    const int k_total = (p.M + WG_BK - 1) / WG_BK;
+    const int it0 = split * p.kiters_per_split, it1 = min(k_total, it0 + p.kiters_per_split);
+    const int p0 = pt * 128, q0 = qt * p.q_tile;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = WG_A_BYTES + p.q_atoms * WG_BK * 128;
+            for (int it = it0; it < it1; ++it) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a_dst = smem + stage * p.stage_bytes;
+                uint8_t* b_dst = a_dst + WG_A_BYTES;
+                mbar_expect_tx(&full[stage], tx);
+                tma_load_2d(a_dst, &tmA, &full[stage], p0, it * WG_BK);
+                tma_load_2d(a_dst + WG_BK * 128, &tmA, &full[stage], p0 + 64, it * WG_BK);
+                for (int a = 0; a < p.q_atoms; ++a)
+                    tma_load_2d(b_dst + a * WG_BK * 128, &tmB, &full[stage], q0 + a * 64, it * WG_BK);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = it0; it < it1; ++it) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
+                const uint32_t b_addr = a_addr + WG_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < WG_BK / 16; ++k) {  // 16 tokens per MMA = two 8-token groups = 2048 B
+                    umma_f16(tmem_base, umma_desc_mnmajor_sw128(a_addr + k * 2048, WG_BK * 128),
+                             umma_desc_mnmajor_sw128(b_addr + k * 2048, WG_BK * 128), p.idesc, (it > it0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        const int lane_grp = warp & 3;
+        const int r = lane_grp * 32 + lane;  // row of the P tile
+        float* dst = p.ws + (static_cast<long long>(split) * p.p_tiles * 128 + p0 + r) * (static_cast<long long>(p.q_tiles) * p.q_tile) + q0;
+        if (it1 > it0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+            for (int c = 0; c < p.q_tile; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(t_row + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    reinterpret_cast<float4*>(dst + c)[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
+                                                                        __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+            }
+        } else {  // empty split (token count not divisible): contribute zeros
+            for (int c = 0; c < p.q_tile; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+}
+
+// out[p, q] = alpha * sum_s ws[s][p][q] + beta * out[p, q]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int P, int Q, int P_pad, int Q_pad,
+                                    int splits, long long ldo, float alpha, float beta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(P) * Q) return;
+    const int q = static_cast<int>(i % Q);
+    const int pr = static_cast<int>(i / Q);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(static_cast<long long>(s) * P_pad + pr) * Q_pad + q];
+    float* o = out + pr * ldo + q;
+    *o = alpha * acc + (beta != 0.f ? beta * *o : 0.f);
+}
+
+}  // namespace ctrl
+
+using namespace ctrl;
+
+extern "C" int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b, long long ldb, int m, int p_dim, int q_dim,
+                                    float* out, long long ldo, float alpha, float beta, float* ws, long long ws_bytes,
+                                    void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !b || !out || !ws || p_dim % 8 || q_dim % 8 || lda % 8 || ldb % 8 || m <= 0) return CTRLORA_ERR_ARG;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = p_dim; p.Q = q_dim; p.M = m;
+    p.q_tile = q_dim >= 256 ? 256 : ((q_dim + 63) / 64) * 64;
+    p.q_atoms = p.q_tile / 64;
+    p.p_tiles = (p_dim + 127) / 128;
+    p.q_tiles = (q_dim + p.q_tile - 1) / p.q_tile;
+    const int k_total = (m + WG_BK - 1) / WG_BK;
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // enough token splits to fill the machine about twice, at least 8 k-iterations each, within the workspace
+    int splits = (2 * sms + p.p_tiles * p.q_tiles - 1) / (p.p_tiles * p.q_tiles);
+    if (splits > k_total / 8) splits = k_total / 8;
+    if (splits < 1) splits = 1;
+    const long long slice = static_cast<long long>(p.p_tiles) * 128 * p.q_tiles * p.q_tile * 4;
+    if (slice > ws_bytes) return CTRLORA_ERR_ARG;
+    if (splits * slice > ws_bytes) splits = static_cast<int>(ws_bytes / slice);
+    p.kiters_per_split = (k_total + splits - 1) / splits;
+    p.splits = (k_total + p.kiters_per_split - 1) / p.kiters_per_split;
+    p.stage_bytes = WG_A_BYTES + p.q_atoms * WG_BK * 128;
+    p.idesc = umma_idesc_f16(128, p.q_tile, 0) | (1u << 15) | (1u << 16);  // A and B MN-major
+    p.ws = ws;
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[2] = {(uint64_t)p_dim, (uint64_t)m};
+        uint64_t str[1] = {(uint64_t)lda * 2};
+        uint32_t box[2] = {64, WG_BK};
+        int rc = make_tmap_f16(&tmA, a, 2, dims, str, box);
+        if (rc) return rc;
+        uint64_t dimsb[2] = {(uint64_t)q_dim, (uint64_t)m};
+        uint64_t strb[1] = {(uint64_t)ldb * 2};
+        rc = make_tmap_f16(&tmB, b, 2, dimsb, strb, box);
+        if (rc) return rc;
+    }
+    p.stages = (200 * 1024) / p.stage_bytes;
+    if (p.stages > WG_STAGES) p.stages = WG_STAGES;
+    const int smem_bytes = p.stages * p.stage_bytes + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(wgrad_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1280) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    if (launch_pdl(wgrad_tn_kernel, dim3(p.p_tiles * p.q_tiles, p.splits), dim3(WG_THREADS), (size_t)smem_bytes, stream, tmA,
+                   tmB, p) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
+    const long long total = static_cast<long long>(p_dim) * q_dim;
+    if (launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, stream,
+                   (const float*)ws, out, p_dim, q_dim, p.p_tiles * 128, p.q_tiles * p.q_tile, p.splits, ldo, alpha, beta) !=
+        cudaSuccess)
+        return CTRLORA_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}

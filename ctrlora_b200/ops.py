@@ -319,3 +319,20 @@ def ddim_update(x, e_cond, e_uncond, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_m
                                           float(sigma_t), float(sqrt_one_minus_at), float(temperature), _sp()),
           "ddim_update")
     return x_prev, pred_x0
+
+
+def wgrad_tn(a, b, out=None, alpha=1.0, beta=0.0):
+    """out[p, q] = alpha * sum_m a[m, p] * b[m, q] + beta * out  (fp16 a [M,P], b [M,Q] -> fp32 [P,Q])."""
+    _require_cuda(a, b)
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and a.stride(1) == 1 and b.stride(1) == 1
+    m, pd = a.shape
+    qd = b.shape[1]
+    assert b.shape[0] == m
+    if out is None:
+        assert beta == 0.0
+        out = torch.empty((pd, qd), device=a.device, dtype=torch.float32)
+    ws, _ = _splitk_buffers(a.device)
+    _count(2)
+    check(_lib.load().ctrlora_wgrad_tn_f16(_dp(a), a.stride(0), _dp(b), b.stride(0), m, pd, qd, _dp(out), out.stride(0),
+                                           float(alpha), float(beta), _dp(ws), SPLITK_WS_BYTES, _sp()), "ctrlora_wgrad_tn_f16")
+    return out

@@ -136,6 +136,16 @@ int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_unco
                         float* pred_x0, float* stats, int batch, int per_image, float cfg_scale, float a_t, float a_prev,
                         float sigma_t, float sqrt_one_minus_at, float temperature, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training (backward of the trainable set; reference: autograd over cldm/lora.py:70-80,285-291 and cldm/cldm.py:281-282,
+ * parameters selected by cldm/cldm_ctrlora_finetune.py:88-100).
+ *
+ * Weight-gradient GEMM over the token dimension: out[p, q] = alpha * sum_m a[m, p] * b[m, q] + beta * out[p, q],
+ * fp16 a [m, p_dim] (row stride lda), b [m, q_dim] (ldb), fp32 out (row stride ldo).  ws: fp32 scratch (any contents).
+ */
+int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b, long long ldb, int m, int p_dim, int q_dim, float* out,
+                         long long ldo, float alpha, float beta, float* ws, long long ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
