@@ -79,6 +79,16 @@ _ARGTYPES = {
     "ctrlora_cast_transpose_f32_to_f16": [_P, _P, _L, _I, _I, _P],
     "ctrlora_ddim_update": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P],
     "ctrlora_wgrad_tn_f16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _F, _F, _P, _L, _P],
+    "ctrlora_groupnorm_bwd_f16": [_P, _P, _P, _P, _L, _F, _P, _L, _F, _P, _P, _P],
+    "ctrlora_layernorm_bwd_f16": [_P, _L, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P],
+    "ctrlora_geglu_fwd_f16": [_P, _P, _L, _I, _P],
+    "ctrlora_geglu_bwd_f16": [_P, _P, _P, _L, _I, _P],
+    "ctrlora_colsum": [_P, _I, _L, _L, _I, _F, _P, _P],
+    "ctrlora_image_colsum_f16": [_P, _L, _I, _I, _I, _P, _L, _P],
+    "ctrlora_upsample2x_bwd_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "ctrlora_im2col_s2_bwd_f16": [_P, _P, _I, _I, _I, _I, _P],
+    "ctrlora_mse_loss_grad": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "ctrlora_adamw_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
 }
 
 
@@ -116,4 +126,14 @@ EXPORTS = [
     "ctrlora_cast_transpose_f32_to_f16",
     "ctrlora_ddim_update",
     "ctrlora_wgrad_tn_f16",
+    "ctrlora_groupnorm_bwd_f16",
+    "ctrlora_layernorm_bwd_f16",
+    "ctrlora_geglu_fwd_f16",
+    "ctrlora_geglu_bwd_f16",
+    "ctrlora_colsum",
+    "ctrlora_image_colsum_f16",
+    "ctrlora_upsample2x_bwd_f16",
+    "ctrlora_im2col_s2_bwd_f16",
+    "ctrlora_mse_loss_grad",
+    "ctrlora_adamw_f32",
 ]

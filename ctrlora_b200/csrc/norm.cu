@@ -249,3 +249,265 @@ extern "C" int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long
     else launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), (size_t)0, stream, xp, ldx, yp, ldy, rows, cols, gamma, beta, eps);
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
+
+// ================================================================================================ backward (training)
+// GroupNorm(+SiLU) backward.  Forward: z = xhat * gamma + beta, y = silu(z) (or z); xhat = (x - mu) * rstd per (image,
+// group).  With dz = dy * silu'(z):  dx = rstd * (dz*gamma - mean_g(dz*gamma) - xhat * mean_g(dz*gamma*xhat)),
+// dgamma_c = sum dz*xhat, dbeta_c = sum dz.  x is re-read through the same (concat, addend) source description as the
+// forward; mu/rstd come from the forward's saved {sum, sumsq}.
+namespace ctrl {
+
+__device__ __forceinline__ float dsilu_f(float z) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+__device__ __forceinline__ void load8h(const __half* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+// bstats[b][g] = {sum dz*gamma, sum dz*gamma*xhat}; optional dgamma/dbeta accumulation (fp32 atomics, one per channel per block)
+__global__ void __launch_bounds__(512)
+gn_bwd_stats_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int groups, int pix_per_block,
+                    const float* __restrict__ fstats, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                    int silu, float* __restrict__ bstats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm[];  // [2][C]: sum dz, sum dz*xhat per channel
+    float* c_dz = sm;
+    float* c_dzx = sm + C;
+    const int b = blockIdx.y;
+    const int vecs = C >> 3, lanes = blockDim.x / vecs;
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int cpg = C / groups;
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * HW);
+    if (pl < lanes) {
+        float mu[8], rs[8], ga[8], be[8], a[8], q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = vec * 8 + e, g = c / cpg;
+            const float mean = fstats[(b * groups + g) * 2] * inv_n;
+            const float var = fmaxf(fstats[(b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+            mu[e] = mean; rs[e] = rsqrtf(var + eps); ga[e] = gamma[c]; be[e] = beta[c]; a[e] = 0.f; q[e] = 0.f;
+        }
+        const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+        for (int p = p0 + pl; p < p1; p += lanes) {
+            const long long pix = static_cast<long long>(b) * HW + p;
+            float x[8], d[8];
+            load8(s, pix, vec * 8, x);
+            load8h(dy + pix * C + vec * 8, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float xh = (x[e] - mu[e]) * rs[e];
+                const float dz = silu ? d[e] * dsilu_f(xh * ga[e] + be[e]) : d[e];
+                a[e] += dz; q[e] += dz * xh;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { atomicAdd(&c_dz[vec * 8 + e], a[e]); atomicAdd(&c_dzx[vec * 8 + e], q[e]); }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float g1 = 0.f, g2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { g1 += gamma[c] * c_dz[c]; g2 += gamma[c] * c_dzx[c]; }
+        atomicAdd(&bstats[(b * groups + g) * 2], g1);
+        atomicAdd(&bstats[(b * groups + g) * 2 + 1], g2);
+    }
+    if (dgamma) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(&dgamma[c], c_dzx[c]); atomicAdd(&dbeta[c], c_dz[c]); }
+    }
+}
+
+__global__ void __launch_bounds__(512)
+gn_bwd_apply_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int groups, int pix_per_block,
+                    const float* __restrict__ fstats, const float* __restrict__ bstats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int silu, __half* __restrict__ dx1, long long ldd1, float scale1,
+                    __half* __restrict__ dx2, long long ldd2, float scale2) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int vecs = C >> 3, lanes = blockDim.x / vecs;
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    if (pl >= lanes) return;
+    const int cpg = C / groups;
+    const float inv_n = 1.0f / (static_cast<float>(cpg) * HW);
+    float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = vec * 8 + e, g = c / cpg;
+        const float mean = fstats[(b * groups + g) * 2] * inv_n;
+        const float var = fmaxf(fstats[(b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+        mu[e] = mean; rs[e] = rsqrtf(var + eps); ga[e] = gamma[c]; be[e] = beta[c];
+        m1[e] = bstats[(b * groups + g) * 2] * inv_n; m2[e] = bstats[(b * groups + g) * 2 + 1] * inv_n;
+    }
+    const bool first = vec * 8 < s.c1;
+    __half* dst = first ? dx1 : dx2;
+    if (!dst) return;
+    const long long ldd = first ? ldd1 : ldd2;
+    const int coff = first ? vec * 8 : vec * 8 - s.c1;
+    const float osc = first ? scale1 : scale2;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    for (int p = p0 + pl; p < p1; p += lanes) {
+        const long long pix = static_cast<long long>(b) * HW + p;
+        float x[8], d[8];
+        load8(s, pix, vec * 8, x);
+        load8h(dy + pix * C + vec * 8, d);
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (x[e] - mu[e]) * rs[e];
+            const float dz = silu ? d[e] * dsilu_f(xh * ga[e] + be[e]) : d[e];
+            o[e] = osc * rs[e] * (dz * ga[e] - m1[e] - xh * m2[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+        *reinterpret_cast<uint4*>(dst + pix * ldd + coff) = u;
+    }
+}
+
+// LayerNorm backward: one warp per row (grid-stride), dgamma/dbeta accumulated per lane then once per block.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ dy, long long ldy,
+                     __half* __restrict__ dx, long long lddx, int M, int C, const float* __restrict__ gamma, float eps,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm[];  // [2][C] when dgamma
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int vecs = C >> 3;
+    float agam[MAXV][8], abet[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { agam[i][e] = 0.f; abet[i][e] = 0.f; }
+    for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+        float v[MAXV][8], d[MAXV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < vecs) {
+                load8h(x + row * ldx + vi * 8, v[i]);
+                load8h(dy + row * ldy + vi * 8, d[i]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sum += v[i][e];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / C;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (lane + i * 32 < vecs)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float t = v[i][e] - mean; sq += t * t; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / C + eps);
+        float s1 = 0.f, s2 = 0.f;  // sum dz, sum dz*xhat with dz = dy*gamma
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < vecs) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (v[i][e] - mean) * rstd;
+                    const float dz = d[i][e] * gamma[vi * 8 + e];
+                    s1 += dz; s2 += dz * xh;
+                    agam[i][e] += d[i][e] * xh; abet[i][e] += d[i][e];
+                    v[i][e] = xh; d[i][e] = dz;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        s1 /= C; s2 /= C;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < vecs) {
+                uint4 u;
+                __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    h[e] = __floats2half2_rn(rstd * (d[i][2 * e] - s1 - v[i][2 * e] * s2),
+                                             rstd * (d[i][2 * e + 1] - s1 - v[i][2 * e + 1] * s2));
+                *reinterpret_cast<uint4*>(dx + row * lddx + vi * 8) = u;
+            }
+        }
+    }
+    if (dgamma) {
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < vecs)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { atomicAdd(&sm[vi * 8 + e], agam[i][e]); atomicAdd(&sm[C + vi * 8 + e], abet[i][e]); }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { atomicAdd(&dgamma[c], sm[c]); atomicAdd(&dbeta[c], sm[C + c]); }
+    }
+}
+
+}  // namespace ctrl
+
+extern "C" int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* a, const void* dy, const void* fwd_stats, void* dx1,
+                                         long long ldd1, float dx1_scale, void* dx2, long long ldd2, float dx2_scale,
+                                         float* dgamma, float* dbeta, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!a || !a->x1 || !dy || !fwd_stats || !a->stats_ws || !a->gamma || !a->beta) return CTRLORA_ERR_ARG;
+    const int C = a->c1 + (a->x2 ? a->c2 : 0);
+    if (C % 8 != 0 || a->c1 % 8 != 0 || C % a->groups != 0 || C / 8 > 512) return CTRLORA_ERR_ARG;
+    GnSrc s;
+    s.x1 = reinterpret_cast<const __half*>(a->x1); s.add1 = reinterpret_cast<const __half*>(a->add1); s.s1 = a->add1_scale;
+    s.c1 = a->c1; s.ld1 = a->ld1;
+    s.x2 = reinterpret_cast<const __half*>(a->x2); s.add2 = reinterpret_cast<const __half*>(a->add2); s.s2 = a->add2_scale;
+    s.c2 = a->x2 ? a->c2 : 0; s.ld2 = a->ld2;
+    const int HW = a->hw, B = a->batch;
+    if (cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    int chunks = (592 + B - 1) / B;
+    int ppb = (HW + chunks - 1) / chunks;
+    if (ppb < 8) ppb = 8;
+    chunks = (HW + ppb - 1) / ppb;
+    dim3 grid(chunks, B);
+    const int vecs = C / 8;
+    const int lanes = vecs >= 256 ? 1 : 256 / vecs;
+    const int threads = vecs * lanes;
+    gn_bwd_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
+        s, reinterpret_cast<const __half*>(dy), C, HW, a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), a->gamma,
+        a->beta, a->eps, a->silu, reinterpret_cast<float*>(a->stats_ws), dgamma, dbeta);
+    launch_pdl(gn_bwd_apply_kernel, grid, dim3(threads), (size_t)0, stream, s, reinterpret_cast<const __half*>(dy), C, HW,
+               (int)a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), reinterpret_cast<const float*>(a->stats_ws),
+               a->gamma, a->beta, a->eps, (int)a->silu, reinterpret_cast<__half*>(dx1), ldd1, dx1_scale,
+               reinterpret_cast<__half*>(dx2), ldd2, dx2_scale);
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+extern "C" int ctrlora_layernorm_bwd_f16(const void* x, long long ldx, const void* dy, long long ldy, void* dx, long long lddx,
+                                         int rows, int cols, const float* gamma, float eps, float* dgamma, float* dbeta,
+                                         void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!x || !dy || !dx || !gamma || cols % 8 != 0 || cols > 1280 || (dgamma && !dbeta)) return CTRLORA_ERR_ARG;
+    int grid = (rows + 7) / 8;
+    if (grid > 592) grid = 592;
+    const size_t sm = dgamma ? 2 * cols * sizeof(float) : 0;
+    const __half* xp = reinterpret_cast<const __half*>(x);
+    const __half* dp = reinterpret_cast<const __half*>(dy);
+    __half* op = reinterpret_cast<__half*>(dx);
+    if (cols <= 512)
+        launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta);
+    else
+        launch_pdl(layernorm_bwd_kernel<5>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta);
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}

@@ -1,0 +1,273 @@
+// Training-only elementwise / reduction kernels (HBM-bound): GEGLU forward+backward on stored pre-activations, column
+// sums (bias gradients), nearest-upsample and stride-2-gather adjoints, the eps-MSE loss with its gradient, fused AdamW.
+#include "common.cuh"
+#include "ctrlora_b200.h"
+
+namespace ctrl {
+
+__device__ __forceinline__ void ld8(const __half* p, float* v) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+__device__ __forceinline__ void st8(__half* p, const float* v) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// GEGLU on the stored projection h = [value | gate] ([M, 2N]): out = value * gelu(gate)   (attention.py:49-56)
+__global__ void geglu_fwd_kernel(const __half* __restrict__ h, __half* __restrict__ out, long long M, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // one 8-vector
+    const int nv = N >> 3;
+    if (i >= M * nv) return;
+    const long long row = i / nv;
+    const int c = static_cast<int>(i % nv) * 8;
+    float v[8], g[8];
+    ld8(h + row * 2 * N + c, v);
+    ld8(h + row * 2 * N + N + c, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= gelu_erf_f(g[e]);
+    st8(out + row * N + c, v);
+}
+
+// dh = [dout * gelu(gate) | dout * value * gelu'(gate)],  gelu'(g) = Phi(g) + g * phi(g)
+__global__ void geglu_bwd_kernel(const __half* __restrict__ h, const __half* __restrict__ dout, __half* __restrict__ dh,
+                                 long long M, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int nv = N >> 3;
+    if (i >= M * nv) return;
+    const long long row = i / nv;
+    const int c = static_cast<int>(i % nv) * 8;
+    float v[8], g[8], d[8], dv[8], dg[8];
+    ld8(h + row * 2 * N + c, v);
+    ld8(h + row * 2 * N + N + c, g);
+    ld8(dout + row * N + c, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float cdf = 0.5f * (1.0f + erff(g[e] * 0.70710678118654752f));
+        const float pdf = 0.3989422804014327f * __expf(-0.5f * g[e] * g[e]);
+        dv[e] = d[e] * g[e] * cdf;
+        dg[e] = d[e] * v[e] * (cdf + g[e] * pdf);
+    }
+    st8(dh + row * 2 * N + c, dv);
+    st8(dh + row * 2 * N + N + c, dg);
+}
+
+// out[c] (+)= scale * sum_rows x[row, c]     (bias gradients); fp16 or fp32 input, fp32 atomics once per block per column
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long rows, int cols, float scale, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = static_cast<long long>(blockIdx.y) * ((rows + gridDim.y - 1) / gridDim.y);
+    const long long r1 = min(rows, r0 + (rows + gridDim.y - 1) / gridDim.y);
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += static_cast<float>(x[r * ld + c]);
+    atomicAdd(&out[c], scale * acc);
+}
+
+// per-image column sums: out[img, c] = sum over the image's rows (time-embedding gradient of a ResBlock conv)
+__global__ void rowgroup_colsum_kernel(const __half* __restrict__ x, long long ld, int rows_per_img, int cols, float* __restrict__ out,
+                                       long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (c >= cols) return;
+    const int chunk = (rows_per_img + gridDim.z - 1) / gridDim.z;
+    const int r0 = blockIdx.z * chunk, r1 = min(rows_per_img, r0 + chunk);
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += __half2float(x[(static_cast<long long>(img) * rows_per_img + r) * ld + c]);
+    atomicAdd(&out[img * ldo + c], acc);
+}
+
+// adjoint of nearest-2x upsample: din[b,h,w,:] = sum of the 2x2 output block
+__global__ void upsample2x_bwd_kernel(const __half* __restrict__ dout, __half* __restrict__ din, int B, int H, int W, int vecs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * H * W * vecs) return;
+    const int v = static_cast<int>(i % vecs);
+    long long pix = i / vecs;
+    const int w = static_cast<int>(pix % W);
+    pix /= W;
+    const int h = static_cast<int>(pix % H);
+    const int b = static_cast<int>(pix / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            float t[8];
+            ld8(dout + (((static_cast<long long>(b) * 2 * H + 2 * h + dy) * 2 * W + 2 * w + dx) * vecs + v) * 8, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += t[e];
+        }
+    st8(din + i * 8, acc);
+}
+
+// adjoint of the stride-2 3x3 pad-1 gather: dx[b,ih,iw,:] = sum over (oh, ow, tap) that read it of dcol[b,oh,ow,tap,:]
+__global__ void im2col_s2_bwd_kernel(const __half* __restrict__ dcol, __half* __restrict__ dx, int B, int H, int W, int vecs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Ho = H / 2, Wo = W / 2;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * H * W * vecs) return;
+    const int v = static_cast<int>(i % vecs);
+    long long pix = i / vecs;
+    const int iw = static_cast<int>(pix % W);
+    pix /= W;
+    const int ih = static_cast<int>(pix % H);
+    const int b = static_cast<int>(pix / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kh = 0; kh < 3; ++kh) {
+        const int t = ih + 1 - kh;  // 2*oh = ih + 1 - kh
+        if (t < 0 || (t & 1)) continue;
+        const int oh = t >> 1;
+        if (oh >= Ho) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+            const int u = iw + 1 - kw;
+            if (u < 0 || (u & 1)) continue;
+            const int ow = u >> 1;
+            if (ow >= Wo) continue;
+            float tv[8];
+            ld8(dcol + ((((static_cast<long long>(b) * Ho + oh) * Wo + ow) * 9 + kh * 3 + kw) * vecs + v) * 8, tv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += tv[e];
+        }
+    }
+    st8(dx + i * 8, acc);
+}
+
+// loss = mean((eps - noise)^2) over everything (== mean over images of per-image means, ddpm.py:902-918 with logvar 0);
+// grad (pixel-major fp16 [B, HW, c_pad]) = 2 (eps - noise) / numel * grad_scale.  eps, noise: fp32 NCHW.
+__global__ void mse_loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise, float* __restrict__ loss,
+                                     __half* __restrict__ grad, int B, int C, int HW, int c_pad, float grad_scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = static_cast<long long>(B) * C * HW;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float sq = 0.f;
+    if (i < total) {
+        const int p = static_cast<int>(i % HW);
+        const int c = static_cast<int>((i / HW) % C);
+        const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+        const float d = eps[i] - noise[i];
+        sq = d * d;
+        grad[(static_cast<long long>(b) * HW + p) * c_pad + c] = __float2half_rn(2.0f * d / static_cast<float>(total) * grad_scale);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(loss, sq / static_cast<float>(total));
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction), fp32 master params, one flat buffer.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                             float grad_scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+}
+
+static inline unsigned nblk(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace ctrl
+
+using namespace ctrl;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA)
+
+extern "C" int ctrlora_geglu_fwd_f16(const void* h, void* out, long long rows, int n, void* stream) {
+    if (!h || !out || n % 8) return CTRLORA_ERR_ARG;
+    launch_pdl(geglu_fwd_kernel, dim3(nblk(rows * (n / 8), 256)), dim3(256), (size_t)0, STREAM(stream),
+               reinterpret_cast<const __half*>(h), reinterpret_cast<__half*>(out), rows, n);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_geglu_bwd_f16(const void* h, const void* dout, void* dh, long long rows, int n, void* stream) {
+    if (!h || !dout || !dh || n % 8) return CTRLORA_ERR_ARG;
+    launch_pdl(geglu_bwd_kernel, dim3(nblk(rows * (n / 8), 256)), dim3(256), (size_t)0, STREAM(stream),
+               reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(dout), reinterpret_cast<__half*>(dh), rows, n);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_colsum(const void* x, int x_is_f32, long long ld, long long rows, int cols, float scale, float* out,
+                              void* stream) {
+    if (!x || !out) return CTRLORA_ERR_ARG;
+    int ysplit = static_cast<int>(rows / 256);
+    if (ysplit < 1) ysplit = 1;
+    if (ysplit > 64) ysplit = 64;
+    dim3 grid((cols + 127) / 128, ysplit);
+    if (x_is_f32)
+        launch_pdl(colsum_kernel<float>, grid, dim3(128), (size_t)0, STREAM(stream), reinterpret_cast<const float*>(x), ld, rows, cols, scale, out);
+    else
+        launch_pdl(colsum_kernel<__half>, grid, dim3(128), (size_t)0, STREAM(stream), reinterpret_cast<const __half*>(x), ld, rows, cols, scale, out);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_image_colsum_f16(const void* x, long long ld, int images, int rows_per_img, int cols, float* out,
+                                        long long ldo, void* stream) {
+    if (!x || !out) return CTRLORA_ERR_ARG;
+    int z = rows_per_img / 128;
+    if (z < 1) z = 1;
+    if (z > 32) z = 32;
+    dim3 grid((cols + 127) / 128, images, z);
+    launch_pdl(rowgroup_colsum_kernel, grid, dim3(128), (size_t)0, STREAM(stream), reinterpret_cast<const __half*>(x), ld,
+               rows_per_img, cols, out, ldo);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_upsample2x_bwd_f16(const void* dout, void* din, int batch, int h, int w, int channels, void* stream) {
+    if (!dout || !din || channels % 8) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    launch_pdl(upsample2x_bwd_kernel, dim3(nblk(static_cast<long long>(batch) * h * w * vecs, 256)), dim3(256), (size_t)0,
+               STREAM(stream), reinterpret_cast<const __half*>(dout), reinterpret_cast<__half*>(din), batch, h, w, vecs);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_im2col_s2_bwd_f16(const void* dcol, void* dx, int batch, int h, int w, int channels, void* stream) {
+    if (!dcol || !dx || channels % 8 || (h & 1) || (w & 1)) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    launch_pdl(im2col_s2_bwd_kernel, dim3(nblk(static_cast<long long>(batch) * h * w * vecs, 256)), dim3(256), (size_t)0,
+               STREAM(stream), reinterpret_cast<const __half*>(dcol), reinterpret_cast<__half*>(dx), batch, h, w, vecs);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_mse_loss_grad(const float* eps, const float* noise, float* loss, void* grad, int batch, int channels,
+                                     int hw, int c_pad, float grad_scale, void* stream) {
+    if (!eps || !noise || !loss || !grad || c_pad < channels) return CTRLORA_ERR_ARG;
+    if (cudaMemsetAsync(loss, 0, sizeof(float), STREAM(stream)) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    if (cudaMemsetAsync(grad, 0, static_cast<size_t>(batch) * hw * c_pad * 2, STREAM(stream)) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    const long long total = static_cast<long long>(batch) * channels * hw;
+    mse_loss_grad_kernel<<<nblk(total, 256), 256, 0, STREAM(stream)>>>(eps, noise, loss, reinterpret_cast<__half*>(grad), batch,
+                                                                       channels, hw, c_pad, grad_scale);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                 void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) return CTRLORA_ERR_ARG;
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    adamw_kernel<<<nblk(n, 256), 256, 0, STREAM(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                           weight_decay, bc1, bc2, grad_scale);
+    return LAUNCH_OK();
+}

@@ -146,6 +146,35 @@ int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_unco
 int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b, long long ldb, int m, int p_dim, int q_dim, float* out,
                          long long ldo, float alpha, float beta, float* ws, long long ws_bytes, void* stream);
 
+/* GroupNorm(+SiLU) backward: same source description as the forward (`args`, whose stats_ws is a scratch buffer for the
+ * backward statistics); fwd_stats = the {sum, sumsq} buffer the forward left in ITS stats_ws.  dx1 / dx2: gradients of
+ * the two concat halves (fp16, row strides ldd1 / ldd2, scaled by dx*_scale; dx2 may be NULL).  dgamma/dbeta (fp32 [C],
+ * accumulated into) may be NULL. */
+int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* args, const void* dy, const void* fwd_stats, void* dx1,
+                              long long ldd1, float dx1_scale, void* dx2, long long ldd2, float dx2_scale, float* dgamma,
+                              float* dbeta, void* stream);
+/* LayerNorm backward (statistics recomputed from x); dgamma/dbeta accumulated into (may be NULL). */
+int ctrlora_layernorm_bwd_f16(const void* x, long long ldx, const void* dy, long long ldy, void* dx, long long lddx, int rows,
+                              int cols, const float* gamma, float eps, float* dgamma, float* dbeta, void* stream);
+/* GEGLU on the stored projection h = [value | gate] ([rows, 2n]): out = value * gelu(gate), and its backward. */
+int ctrlora_geglu_fwd_f16(const void* h, void* out, long long rows, int n, void* stream);
+int ctrlora_geglu_bwd_f16(const void* h, const void* dout, void* dh, long long rows, int n, void* stream);
+/* out[c] += scale * sum_rows x[row, c]  (bias gradients); out[img, c] += per-image column sums (time-embedding gradients) */
+int ctrlora_colsum(const void* x, int x_is_f32, long long ld, long long rows, int cols, float scale, float* out, void* stream);
+int ctrlora_image_colsum_f16(const void* x, long long ld, int images, int rows_per_img, int cols, float* out, long long ldo,
+                             void* stream);
+/* adjoints of ctrlora_upsample2x_f16 and ctrlora_im2col_s2_f16 */
+int ctrlora_upsample2x_bwd_f16(const void* dout, void* din, int batch, int h, int w, int channels, void* stream);
+int ctrlora_im2col_s2_bwd_f16(const void* dcol, void* dx, int batch, int h, int w, int channels, void* stream);
+/* loss = mean((eps - noise)^2)  (ldm/models/diffusion/ddpm.py:902-918, logvar = 0) and its gradient, written as
+ * pixel-major fp16 [batch, hw, c_pad] (times grad_scale); eps / noise are fp32 NCHW. */
+int ctrlora_mse_loss_grad(const float* eps, const float* noise, float* loss, void* grad, int batch, int channels, int hw,
+                          int c_pad, float grad_scale, void* stream);
+/* torch.optim.AdamW step over one flat fp32 buffer (cldm/cldm_ctrlora_finetune.py:105: lr 1e-5, betas .9/.999, eps 1e-8,
+ * weight decay 0.01); grads are multiplied by grad_scale first (1/world_size after an all-reduce SUM). */
+int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
