@@ -173,7 +173,7 @@ def _sp():
 
 
 def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None, add2_scale=1.0,
-              groups=32, want_raw=False, stats_ws=None):
+              groups=32, want_raw=False, stats_ws=None, want_stats=False):
     """GroupNorm(+SiLU) over [x1 (+s1*add1) | x2 (+s2*add2)], pixel-major fp16 [B,H,W,C*]; returns y (and raw concat)."""
     _require_cuda(x1, x2, add1, add2)
     b, h, w, c1, ld1 = _as_bhwc(x1)
@@ -198,6 +198,8 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     a.y, a.raw_out, a.stats_ws = _dp(y), _dp(raw), _dp(stats_ws)
     _count(2)
     check(_lib.load().ctrlora_groupnorm_f16(C.addressof(a), _sp()), "ctrlora_groupnorm_f16")
+    if want_stats:
+        return (y, raw, stats_ws) if want_raw else (y, stats_ws)
     return (y, raw) if want_raw else y
 
 
@@ -336,3 +338,126 @@ def wgrad_tn(a, b, out=None, alpha=1.0, beta=0.0):
     check(_lib.load().ctrlora_wgrad_tn_f16(_dp(a), a.stride(0), _dp(b), b.stride(0), m, pd, qd, _dp(out), out.stride(0),
                                            float(alpha), float(beta), _dp(ws), SPLITK_WS_BYTES, _sp()), "ctrlora_wgrad_tn_f16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training kernels
+def _gn_args(x1, gamma, beta, eps, silu, add1, add1_scale, x2, add2, add2_scale, groups, stats_ws):
+    b, h, w, c1, ld1 = _as_bhwc(x1)
+    c2, ld2 = 0, 0
+    if x2 is not None:
+        _, _, _, c2, ld2 = _as_bhwc(x2)
+    a = _lib.GroupNormArgs()
+    a.x1, a.add1, a.add1_scale, a.c1, a.ld1 = _dp(x1), _dp(add1), float(add1_scale), c1, ld1
+    a.x2, a.add2, a.add2_scale, a.c2, a.ld2 = _dp(x2), _dp(add2), float(add2_scale), c2, ld2
+    a.batch, a.hw, a.groups = b, h * w, groups
+    a.gamma, a.beta, a.eps, a.silu = _dp(gamma), _dp(beta), float(eps), int(silu)
+    a.stats_ws = _dp(stats_ws)
+    return a, (b, h, w, c1, c2)
+
+
+def groupnorm_bwd(dy, fwd_stats, x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None,
+                  add2_scale=1.0, groups=32, want_dx2=False, dx2_scale=1.0, dgamma=None, dbeta=None):
+    """Backward of ops.groupnorm (same source description).  Returns dx1 (and dx2 scaled by dx2_scale if want_dx2);
+    dgamma/dbeta (fp32 [C]) are accumulated into when given."""
+    _require_cuda(dy, x1)
+    assert dy.dtype == torch.float16 and dy.is_contiguous()
+    ws = torch.empty_like(fwd_stats)
+    a, (b, h, w, c1, c2) = _gn_args(x1, gamma, beta, eps, silu, add1, add1_scale, x2, add2, add2_scale, groups, ws)
+    dx1 = torch.empty((b, h, w, c1), device=dy.device, dtype=torch.float16)
+    dx2 = torch.empty((b, h, w, c2), device=dy.device, dtype=torch.float16) if (want_dx2 and c2) else None
+    _count(2)
+    check(_lib.load().ctrlora_groupnorm_bwd_f16(C.addressof(a), _dp(dy), _dp(fwd_stats), _dp(dx1), c1, 1.0, _dp(dx2), c2,
+                                                float(dx2_scale), _dp(dgamma), _dp(dbeta), _sp()), "groupnorm_bwd")
+    return (dx1, dx2) if want_dx2 else dx1
+
+
+def layernorm_bwd(x, dy, gamma, eps=1e-5, dgamma=None, dbeta=None):
+    _require_cuda(x, dy)
+    cols = x.shape[-1]
+    x2, d2 = x.reshape(-1, cols), dy.reshape(-1, cols)
+    dx = torch.empty((x2.shape[0], cols), device=x.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_layernorm_bwd_f16(_dp(x2), x2.stride(0), _dp(d2), d2.stride(0), _dp(dx), cols, x2.shape[0],
+                                                cols, _dp(gamma), float(eps), _dp(dgamma), _dp(dbeta), _sp()), "layernorm_bwd")
+    return dx.view(x.shape)
+
+
+def geglu_fwd(h):
+    """h fp16 [M, 2N] = [value | gate] -> value * gelu(gate) [M, N]"""
+    _require_cuda(h)
+    m, n2 = h.shape
+    out = torch.empty((m, n2 // 2), device=h.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_geglu_fwd_f16(_dp(h), _dp(out), m, n2 // 2, _sp()), "geglu_fwd")
+    return out
+
+
+def geglu_bwd(h, dout):
+    _require_cuda(h, dout)
+    m, n2 = h.shape
+    dh = torch.empty_like(h)
+    _count()
+    check(_lib.load().ctrlora_geglu_bwd_f16(_dp(h), _dp(dout), _dp(dh), m, n2 // 2, _sp()), "geglu_bwd")
+    return dh
+
+
+def colsum(x, out, scale=1.0):
+    """out[c] += scale * sum_rows x[row, c]; x fp16/fp32 [rows, cols] (row stride free), out fp32 [cols]"""
+    _require_cuda(x, out)
+    x2 = x.reshape(-1, x.shape[-1])
+    _count()
+    check(_lib.load().ctrlora_colsum(_dp(x2), int(x2.dtype == torch.float32), x2.stride(0), x2.shape[0], x2.shape[1],
+                                     float(scale), _dp(out), _sp()), "colsum")
+    return out
+
+
+def image_colsum(x, images, out):
+    """out[img, c] += sum over the image's rows of x (fp16 [images*rows, cols]); out fp32 [images, >=cols] (row stride free)"""
+    _require_cuda(x, out)
+    x2 = x.reshape(-1, x.shape[-1])
+    _count()
+    check(_lib.load().ctrlora_image_colsum_f16(_dp(x2), x2.stride(0), images, x2.shape[0] // images, x2.shape[1], _dp(out),
+                                               out.stride(0), _sp()), "image_colsum")
+    return out
+
+
+def upsample2x_bwd(dout):
+    _require_cuda(dout)
+    b, h2, w2, c = dout.shape
+    din = torch.empty((b, h2 // 2, w2 // 2, c), device=dout.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_upsample2x_bwd_f16(_dp(dout.contiguous()), _dp(din), b, h2 // 2, w2 // 2, c, _sp()), "upsample2x_bwd")
+    return din
+
+
+def im2col_s2_bwd(dcol, h, w):
+    """dcol fp16 [B, h/2, w/2, 9*C] -> dx [B, h, w, C]"""
+    _require_cuda(dcol)
+    b = dcol.shape[0]
+    c = dcol.shape[-1] // 9
+    dx = torch.empty((b, h, w, c), device=dcol.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_im2col_s2_bwd_f16(_dp(dcol.contiguous()), _dp(dx), b, h, w, c, _sp()), "im2col_s2_bwd")
+    return dx
+
+
+def mse_loss_grad(eps, noise, c_pad=8, grad_scale=1.0):
+    """eps, noise fp32 [B,C,H,W] -> (loss fp32 [1], grad fp16 pixel-major [B,H,W,c_pad])"""
+    _require_cuda(eps, noise)
+    b, c, h, w = eps.shape
+    loss = torch.empty(1, device=eps.device, dtype=torch.float32)
+    grad = torch.empty((b, h, w, c_pad), device=eps.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_mse_loss_grad(_dp(eps.contiguous()), _dp(noise.contiguous()), _dp(loss), _dp(grad), b, c, h * w,
+                                            c_pad, float(grad_scale), _sp()), "mse_loss_grad")
+    return loss, grad
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+               grad_scale=1.0):
+    """In-place AdamW over flat fp32 buffers (torch.optim.AdamW semantics)."""
+    _require_cuda(params, grads)
+    _count()
+    check(_lib.load().ctrlora_adamw_f32(_dp(params), _dp(grads), _dp(exp_avg), _dp(exp_avg_sq), params.numel(), float(lr),
+                                        float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                        float(grad_scale), _sp()), "adamw")
