@@ -69,7 +69,8 @@ _ARGTYPES = {
     "ctrlora_gemm_f16_simt": [_P, _P],
     "ctrlora_groupnorm_f16": [_P, _P],
     "ctrlora_layernorm_f16": [_P, _L, _P, _L, _I, _I, _P, _P, _F, _P],
-    "ctrlora_attention_f16": [_P, _L, _P, _L, _P, _I, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ctrlora_attention_f16": [_P, _L, _P, _L, _P, _I, _P, _L, _P, _I, _I, _I, _I, _I, _P],
+    "ctrlora_attention_bwd_f16": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P],
     "ctrlora_nchw_f32_to_nhwc_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_nhwc_to_nchw_f32": [_P, _I, _L, _P, _I, _I, _I, _P],
     "ctrlora_timestep_embedding": [_P, _P, _P, _I, _I, _P],
@@ -126,6 +127,7 @@ EXPORTS = [
     "ctrlora_cast_transpose_f32_to_f16",
     "ctrlora_ddim_update",
     "ctrlora_wgrad_tn_f16",
+    "ctrlora_attention_bwd_f16",
     "ctrlora_groupnorm_bwd_f16",
     "ctrlora_layernorm_bwd_f16",
     "ctrlora_geglu_fwd_f16",

@@ -1,0 +1,511 @@
+// Attention backward on tcgen05 (training): given Q, K, V, O, dO and the forward's log-sum-exp, produce dQ, dK, dV.
+// reference: autograd through CrossAttention.forward, ldm/modules/attention.py:163-194.
+//
+// Two kernels, no atomics (fp32 global atomics were measured at ~40 G/s on this part, far too slow for dQ):
+//   attn_bwd_dq_kernel    CTA = 128 queries of one (image, head); loops over key tiles:
+//                           S = Q K^T, dP = dO V^T (UMMA) -> P = exp2(S c - lse), dS = P (dP - D) (row threads)
+//                           -> dQ += dS K (UMMA, K tile re-read as an MN-major B operand)
+//   attn_bwd_dkdv_kernel  CTA = 128 keys of one (image, head); loops over query tiles:
+//                           S^T = K Q^T, dP^T = V dO^T (UMMA) -> P^T, dS^T (thread = key row, lse/D per column)
+//                           -> dV += P^T dO, dK += dS^T Q (UMMA, the Q / dO tiles re-read as MN-major B operands)
+// The same [rows][64-col] SWIZZLE_128B TMA tiles serve both as K-major operands (contraction over d) and as MN-major
+// operands (contraction over tokens); only the UMMA descriptor differs.  D = rowsum(dO * O) comes from a small pre-pass.
+#include "common.cuh"
+#include "ctrlora_b200.h"
+#include "gemm_sm100.cuh"
+
+namespace ctrl {
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+struct AttnBwdParams {
+    int Nq, Nk, heads, d, d16, nkc;
+    float scale, scale_log2e;
+    const float* lse;    // [B, H, Nq]  log2-domain: P = exp2(s * scale_log2e - lse)
+    const float* delta;  // [B, H, Nq]  rowsum(dO * O)
+    __half* dq; long long lddq;
+    __half* dk; long long lddk;
+    __half* dv; long long lddv;
+    uint32_t idesc_s;    // M=128, N = tile width (keys for dq kernel, queries for dkdv kernel), K-major operands
+    uint32_t idesc_acc;  // M=128, N = d16, A K-major, B MN-major
+};
+
+constexpr int AB_THREADS = 192;  // warps 0-3: row threads, warp 4: TMA, warp 5: MMA
+
+// write 32 fp16 values (packed pairs) of row r, columns [c, c+32) of a K-major SWIZZLE_128B operand tile made of
+// 64-column chunks of `rows` rows each
+__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int rows, int r, int c, const uint32_t* packed) {
+    uint8_t* chunk = tile + (c >> 6) * rows * 128 + r * 128;
+    const int u0 = (c & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        uint4 val = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = val;
+    }
+}
+
+// ================================================================================================ D = rowsum(dO * O)
+__global__ void attn_bwd_delta_kernel(const __half* __restrict__ o, long long ldo, const __half* __restrict__ dout, long long lddo,
+                                      float* __restrict__ delta, int batch, int heads, int nq, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, q, h)
+    if (i >= static_cast<long long>(batch) * nq * heads) return;
+    const int h = static_cast<int>(i % heads);
+    const long long row = i / heads;  // b * nq + q
+    const int b = static_cast<int>(row / nq), q = static_cast<int>(row % nq);
+    const __half* op = o + row * ldo + h * d;
+    const __half* dp = dout + row * lddo + h * d;
+    float acc = 0.f;
+    for (int c = 0; c < d; c += 8) {
+        uint4 u = *reinterpret_cast<const uint4*>(op + c), w = *reinterpret_cast<const uint4*>(dp + c);
+        const __half2* a = reinterpret_cast<const __half2*>(&u);
+        const __half2* bb = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = __half22float2(a[e]), y = __half22float2(bb[e]);
+            acc += x.x * y.x + x.y * y.y;
+        }
+    }
+    delta[(static_cast<long long>(b) * heads + h) * nq + q] = acc;
+}
+
+// ================================================================================================ dQ
+template <int DPAD, int BKV>
+struct DqSmem {
+    static constexpr int NKC = (DPAD + 63) / 64;
+    static constexpr int Q_BYTES = NKC * 128 * 128;      // Q and dO: [nkc][128 q][128 B]
+    static constexpr int KV_BYTES = NKC * BKV * 128;     // K and V:  [nkc][BKV keys][128 B]
+    static constexpr int DS_BYTES = (BKV / 64) * 128 * 128 > 0 ? (BKV / 64) * 128 * 128 : 128 * 128;
+    static constexpr int OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_DS = OFF_V + KV_BYTES;
+    static constexpr int DATA = OFF_DS + DS_BYTES;
+    static constexpr int TOTAL = DATA + 1024 + 128;
+};
+
+template <int DPAD, int BKV>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ AttnBwdParams p) {
+    using L = DqSmem<DPAD, BKV>;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem, *sDO = smem + L::OFF_DO, *sK = smem + L::OFF_K, *sV = smem + L::OFF_V, *sDS = smem + L::OFF_DS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA);
+    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *ds_full = bars + 4, *acc_done = bars + 5;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    if (warp == 5 && lane == 0) {
+        mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(s_full, 1);
+        mbar_init(ds_full, 128); mbar_init(acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + BKV, tm_dq = tmem_base + 2 * BKV;
+    const int n_tiles = (p.Nk + BKV - 1) / BKV;
+    const int ksteps_d = (p.d + 15) / 16;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * p.nkc * 128 * 128);
+            for (int kc = 0; kc < p.nkc; ++kc) {
+                tma_load_4d(sQ + kc * 128 * 128, &tmQ, q_full, kc * 64, head, q0, img);
+                tma_load_4d(sDO + kc * 128 * 128, &tmDO, q_full, kc * 64, head, q0, img);
+            }
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j > 0) mbar_wait(kv_free, (j - 1) & 1);
+                mbar_expect_tx(kv_full, 2 * p.nkc * BKV * 128);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    tma_load_4d(sK + kc * BKV * 128, &tmK, kv_full, kc * 64, head, j * BKV, img);
+                    tma_load_4d(sV + kc * BKV * 128, &tmV, kv_full, kc * 64, head, j * BKV, img);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                mbar_wait(kv_full, j & 1);
+                if (j > 0) mbar_wait(ds_full, (j - 1) & 1);  // S / dP of the previous tile have been read out
+                tc_fence_after();
+                const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), ka = smem_u32(sK), va = smem_u32(sV);
+                for (int ks = 0; ks < ksteps_d; ++ks) {
+                    const uint32_t oq = (ks >> 2) * 128 * 128 + (ks & 3) * 32, ok = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
+                    umma_f16(tm_s, umma_desc_kmajor_sw128(qa + oq), umma_desc_kmajor_sw128(ka + ok), p.idesc_s, ks ? 1u : 0u);
+                }
+                for (int ks = 0; ks < ksteps_d; ++ks) {
+                    const uint32_t oq = (ks >> 2) * 128 * 128 + (ks & 3) * 32, ok = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
+                    umma_f16(tm_dp, umma_desc_kmajor_sw128(doa + oq), umma_desc_kmajor_sw128(va + ok), p.idesc_s, ks ? 1u : 0u);
+                }
+                umma_commit(s_full);
+                mbar_wait(ds_full, j & 1);  // dS tile written
+                tc_fence_after();
+                const uint32_t dsa = smem_u32(sDS);
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {  // contraction over the keys of this tile
+                    const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    umma_f16(tm_dq, umma_desc_kmajor_sw128(dsa + oa), desc_mn_sw128(ka + ks * 2048, BKV * 128), p.idesc_acc,
+                             (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(kv_free);  // K/V tile and the dS tile are free once these MMAs complete
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const bool row_ok = q0 + r < p.Nq;
+        const long long stat_idx = (static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r;
+        const float lse = row_ok ? p.lse[stat_idx] : 0.f;
+        const float dl = row_ok ? p.delta[stat_idx] : 0.f;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            if (j > 0) mbar_wait(kv_free, (j - 1) & 1);  // previous dQ MMAs have consumed the dS tile
+            const int kv_valid = min(BKV, p.Nk - j * BKV);
+#pragma unroll 1
+            for (int c = 0; c < BKV; c += 32) {
+                uint32_t sr[32], dr[32], packed[16];
+                tmem_ld_32x32(tm_s + lane_off + c, sr);
+                tmem_ld_32x32(tm_dp + lane_off + c, dr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float ds0 = 0.f, ds1 = 0.f;
+                    if (c + i < kv_valid) {
+                        const float pr = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse));
+                        ds0 = pr * (__uint_as_float(dr[i]) - dl);
+                    }
+                    if (c + i + 1 < kv_valid) {
+                        const float pr = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse));
+                        ds1 = pr * (__uint_as_float(dr[i + 1]) - dl);
+                    }
+                    packed[i >> 1] = pack_half2(ds0, ds1);
+                }
+                store_row_chunk(sDS, 128, r, c, packed);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ds_full);
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        __half* out = p.dq + (static_cast<long long>(img) * p.Nq + q0 + r) * p.lddq + head * p.d;
+#pragma unroll
+        for (int c = 0; c < DPAD; c += 16) {
+            if (c < p.d) {
+                uint32_t raw[16];
+                tmem_ld_32x16(tm_dq + lane_off + c, raw);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (c + g * 8 < p.d) {
+                            uint4 u;
+                            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                w[e] = pack_half2(__uint_as_float(raw[g * 8 + 2 * e]) * p.scale, __uint_as_float(raw[g * 8 + 2 * e + 1]) * p.scale);
+                            *reinterpret_cast<uint4*>(out + c + g * 8) = u;
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ================================================================================================ dK, dV
+template <int DPAD, int BQ>
+struct DkvSmem {
+    static constexpr int NKC = (DPAD + 63) / 64;
+    static constexpr int KV_BYTES = NKC * 128 * 128;   // K and V: [nkc][128 keys][128 B]
+    static constexpr int Q_BYTES = NKC * BQ * 128;     // Q and dO: [nkc][BQ queries][128 B]
+    static constexpr int PT_BYTES = (BQ / 64) * 128 * 128;  // P^T and dS^T: [BQ/64][128 keys][128 B]
+    static constexpr int OFF_V = KV_BYTES, OFF_Q = 2 * KV_BYTES, OFF_DO = OFF_Q + Q_BYTES, OFF_PT = OFF_DO + Q_BYTES,
+                         OFF_DST = OFF_PT + PT_BYTES, OFF_STAT = OFF_DST + PT_BYTES;
+    static constexpr int DATA = OFF_STAT + 2 * BQ * 4;
+    static constexpr int BAR = (DATA + 127) / 128 * 128;
+    static constexpr int TOTAL = BAR + 1024 + 128;
+};
+
+template <int DPAD, int BQ>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ AttnBwdParams p) {
+    using L = DkvSmem<DPAD, BQ>;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sK = smem, *sV = smem + L::OFF_V, *sQ = smem + L::OFF_Q, *sDO = smem + L::OFF_DO, *sPT = smem + L::OFF_PT,
+            *sDST = smem + L::OFF_DST;
+    float* sLse = reinterpret_cast<float*>(smem + L::OFF_STAT);
+    float* sDel = sLse + BQ;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    uint64_t *kv_full = bars, *q_full = bars + 1, *q_free = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *acc_done = bars + 5;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    if (warp == 5 && lane == 0) {
+        mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(q_free, 1); mbar_init(s_full, 1);
+        mbar_init(p_full, 128); mbar_init(acc_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tm_s = tmem_base, tm_dp = tmem_base + BQ, tm_dv = tmem_base + 2 * BQ, tm_dk = tm_dv + DPAD;
+    const int n_tiles = (p.Nq + BQ - 1) / BQ;
+    const int ksteps_d = (p.d + 15) / 16;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * p.nkc * 128 * 128);
+            for (int kc = 0; kc < p.nkc; ++kc) {
+                tma_load_4d(sK + kc * 128 * 128, &tmK, kv_full, kc * 64, head, k0, img);
+                tma_load_4d(sV + kc * 128 * 128, &tmV, kv_full, kc * 64, head, k0, img);
+            }
+            for (int i = 0; i < n_tiles; ++i) {
+                if (i > 0) mbar_wait(q_free, (i - 1) & 1);
+                mbar_expect_tx(q_full, 2 * p.nkc * BQ * 128);
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                    tma_load_4d(sQ + kc * BQ * 128, &tmQ, q_full, kc * 64, head, i * BQ, img);
+                    tma_load_4d(sDO + kc * BQ * 128, &tmDO, q_full, kc * 64, head, i * BQ, img);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            mbar_wait(kv_full, 0);
+            for (int i = 0; i < n_tiles; ++i) {
+                mbar_wait(q_full, i & 1);
+                if (i > 0) mbar_wait(p_full, (i - 1) & 1);
+                tc_fence_after();
+                const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), ka = smem_u32(sK), va = smem_u32(sV);
+                for (int ks = 0; ks < ksteps_d; ++ks) {  // S^T = K Q^T
+                    const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
+                    umma_f16(tm_s, umma_desc_kmajor_sw128(ka + ok), umma_desc_kmajor_sw128(qa + oq), p.idesc_s, ks ? 1u : 0u);
+                }
+                for (int ks = 0; ks < ksteps_d; ++ks) {  // dP^T = V dO^T
+                    const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
+                    umma_f16(tm_dp, umma_desc_kmajor_sw128(va + ok), umma_desc_kmajor_sw128(doa + oq), p.idesc_s, ks ? 1u : 0u);
+                }
+                umma_commit(s_full);
+                mbar_wait(p_full, i & 1);
+                tc_fence_after();
+                const uint32_t pta = smem_u32(sPT), dsta = smem_u32(sDST);
+#pragma unroll
+                for (int ks = 0; ks < BQ / 16; ++ks) {  // contraction over the queries of this tile
+                    const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    umma_f16(tm_dv, umma_desc_kmajor_sw128(pta + oa), desc_mn_sw128(doa + ks * 2048, BQ * 128), p.idesc_acc,
+                             (i > 0 || ks > 0) ? 1u : 0u);
+                    umma_f16(tm_dk, umma_desc_kmajor_sw128(dsta + oa), desc_mn_sw128(qa + ks * 2048, BQ * 128), p.idesc_acc,
+                             (i > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(q_free);
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        const int r = warp * 32 + lane;  // key row of this thread
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const bool key_ok = k0 + r < p.Nk;
+        const long long stat_base = (static_cast<long long>(img) * p.heads + head) * p.Nq;
+        for (int i = 0; i < n_tiles; ++i) {
+            if (i > 0) mbar_wait(q_free, (i - 1) & 1);  // previous accumulate MMAs done: P^T / dS^T / stats reusable
+            if (r < BQ) {
+                const int q = i * BQ + r;
+                sLse[r] = q < p.Nq ? p.lse[stat_base + q] : 0.f;
+                sDel[r] = q < p.Nq ? p.delta[stat_base + q] : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+            const int q_valid = min(BQ, p.Nq - i * BQ);
+#pragma unroll 1
+            for (int c = 0; c < BQ; c += 32) {
+                uint32_t sr[32], dr[32], pp[16], dd[16];
+                tmem_ld_32x32(tm_s + lane_off + c, sr);
+                tmem_ld_32x32(tm_dp + lane_off + c, dr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                    if (key_ok && c + t < q_valid) {
+                        p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -sLse[c + t]));
+                        d0 = p0 * (__uint_as_float(dr[t]) - sDel[c + t]);
+                    }
+                    if (key_ok && c + t + 1 < q_valid) {
+                        p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -sLse[c + t + 1]));
+                        d1 = p1 * (__uint_as_float(dr[t + 1]) - sDel[c + t + 1]);
+                    }
+                    pp[t >> 1] = pack_half2(p0, p1);
+                    dd[t >> 1] = pack_half2(d0, d1);
+                }
+                store_row_chunk(sPT, 128, r, c, pp);
+                store_row_chunk(sDST, 128, r, c, dd);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        __half* ov = p.dv + (static_cast<long long>(img) * p.Nk + k0 + r) * p.lddv + head * p.d;
+        __half* okk = p.dk + (static_cast<long long>(img) * p.Nk + k0 + r) * p.lddk + head * p.d;
+#pragma unroll
+        for (int c = 0; c < DPAD; c += 16) {
+            if (c < p.d) {
+                uint32_t rv[16], rk[16];
+                tmem_ld_32x16(tm_dv + lane_off + c, rv);
+                tmem_ld_32x16(tm_dk + lane_off + c, rk);
+                tmem_ld_wait();
+                if (key_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (c + g * 8 < p.d) {
+                            uint4 u, w;
+                            uint32_t* uu = reinterpret_cast<uint32_t*>(&u);
+                            uint32_t* ww = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                uu[e] = pack_half2(__uint_as_float(rv[g * 8 + 2 * e]), __uint_as_float(rv[g * 8 + 2 * e + 1]));
+                                ww[e] = pack_half2(__uint_as_float(rk[g * 8 + 2 * e]) * p.scale, __uint_as_float(rk[g * 8 + 2 * e + 1]) * p.scale);
+                            }
+                            *reinterpret_cast<uint4*>(ov + c + g * 8) = u;
+                            *reinterpret_cast<uint4*>(okk + c + g * 8) = w;
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int DPAD, int BKV>
+static int launch_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                     const AttnBwdParams& p, dim3 grid, cudaStream_t s) {
+    using L = DqSmem<DPAD, BKV>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_bwd_dq_kernel<DPAD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    return launch_pdl(attn_bwd_dq_kernel<DPAD, BKV>, grid, dim3(AB_THREADS), (size_t)L::TOTAL, s, tq, tdo, tk, tv, p) == cudaSuccess
+               ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+template <int DPAD, int BQ>
+static int launch_dkdv(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnBwdParams& p, dim3 grid, cudaStream_t s) {
+    using L = DkvSmem<DPAD, BQ>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_bwd_dkdv_kernel<DPAD, BQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    return launch_pdl(attn_bwd_dkdv_kernel<DPAD, BQ>, grid, dim3(AB_THREADS), (size_t)L::TOTAL, s, tq, tdo, tk, tv, p) == cudaSuccess
+               ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+static int tmap_tokens(CUtensorMap* m, const void* base, long long ld, int d, int heads, int n, int batch, int box_rows) {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)n, (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * n};
+    uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+    return make_tmap_f16(m, base, 4, dims, str, box);
+}
+
+}  // namespace ctrl
+
+using namespace ctrl;
+
+extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                         long long ldv, const void* o, long long ldo, const void* dout, long long lddo,
+                                         const float* lse, float* delta_ws, void* dq, long long lddq, void* dk, long long lddk,
+                                         void* dv, long long lddv, int batch, int heads, int nq, int nk, int head_dim,
+                                         void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (!q || !k || !v || !o || !dout || !lse || !delta_ws || !dq || !dk || !dv) return CTRLORA_ERR_ARG;
+    const int d = head_dim;
+    if (d % 8 || d > 160 || ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || lddo % 8 || lddq % 8 || lddk % 8 || lddv % 8)
+        return CTRLORA_ERR_ARG;
+    {
+        const long long total = static_cast<long long>(batch) * nq * heads;
+        launch_pdl(attn_bwd_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, stream,
+                   reinterpret_cast<const __half*>(o), ldo, reinterpret_cast<const __half*>(dout), lddo, delta_ws, batch, heads, nq, d);
+    }
+    AttnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.Nq = nq; p.Nk = nk; p.heads = heads; p.d = d; p.d16 = (d + 15) / 16 * 16; p.nkc = (d + 63) / 64;
+    p.scale = 1.0f / sqrtf(static_cast<float>(d));
+    p.scale_log2e = p.scale * 1.4426950408889634f;
+    p.lse = lse; p.delta = delta_ws;
+    p.dq = reinterpret_cast<__half*>(dq); p.lddq = lddq;
+    p.dk = reinterpret_cast<__half*>(dk); p.lddk = lddk;
+    p.dv = reinterpret_cast<__half*>(dv); p.lddv = lddv;
+    p.idesc_acc = umma_idesc_f16(128, p.d16, 0) | (1u << 16);  // B operand MN-major
+    const bool wide = d > 80;
+    // ---- dQ: 128-query CTAs, key tiles of 128 (64 for d_head 160)
+    {
+        const int bkv = wide ? 64 : 128;
+        CUtensorMap tq, tdo, tk, tv;
+        int rc = tmap_tokens(&tq, q, ldq, d, heads, nq, batch, 128);
+        if (!rc) rc = tmap_tokens(&tdo, dout, lddo, d, heads, nq, batch, 128);
+        if (!rc) rc = tmap_tokens(&tk, k, ldk, d, heads, nk, batch, bkv);
+        if (!rc) rc = tmap_tokens(&tv, v, ldv, d, heads, nk, batch, bkv);
+        if (rc) return rc;
+        p.idesc_s = umma_idesc_f16(128, bkv, 0);
+        dim3 grid((nq + 127) / 128, heads, batch);
+        if (d <= 48) rc = launch_dq<48, 128>(tq, tdo, tk, tv, p, grid, stream);
+        else if (d <= 80) rc = launch_dq<80, 128>(tq, tdo, tk, tv, p, grid, stream);
+        else rc = launch_dq<160, 64>(tq, tdo, tk, tv, p, grid, stream);
+        if (rc) return rc;
+    }
+    // ---- dK, dV: 128-key CTAs, query tiles of 128 (64 for d_head 160)
+    {
+        const int bq = wide ? 64 : 128;
+        CUtensorMap tq, tdo, tk, tv;
+        int rc = tmap_tokens(&tq, q, ldq, d, heads, nq, batch, bq);
+        if (!rc) rc = tmap_tokens(&tdo, dout, lddo, d, heads, nq, batch, bq);
+        if (!rc) rc = tmap_tokens(&tk, k, ldk, d, heads, nk, batch, 128);
+        if (!rc) rc = tmap_tokens(&tv, v, ldv, d, heads, nk, batch, 128);
+        if (rc) return rc;
+        p.idesc_s = umma_idesc_f16(128, bq, 0);
+        dim3 grid((nk + 127) / 128, heads, batch);
+        if (d <= 48) rc = launch_dkdv<48, 128>(tq, tdo, tk, tv, p, grid, stream);
+        else if (d <= 80) rc = launch_dkdv<80, 128>(tq, tdo, tk, tv, p, grid, stream);
+        else rc = launch_dkdv<160, 64>(tq, tdo, tk, tv, p, grid, stream);
+        if (rc) return rc;
+    }
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}

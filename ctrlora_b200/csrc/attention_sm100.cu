@@ -26,6 +26,7 @@ struct AttnParams {
     float scale_log2e;          // d^-1/2 * log2(e)
     __half* out;
     long long ldo;
+    float* lse;                 // optional [B, H, Nq]: log2-domain log-sum-exp, for the backward
     uint32_t idesc_s, idesc_pv, idesc_l;
 };
 
@@ -266,8 +267,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t lfin;
         tmem_ld_32x1(tmem_l + lane_off, lfin);
         tmem_ld_wait();
-        const float inv_l = 1.0f / (l_run + __uint_as_float(lfin));
+        const float l_tot = l_run + __uint_as_float(lfin);
+        const float inv_l = 1.0f / l_tot;
         const bool row_ok = (q0 + r) < p.Nq;
+        if (p.lse && row_ok)
+            p.lse[(static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r] = m_run * p.scale_log2e + log2f(l_tot);
         __half* orow = p.out + (static_cast<long long>(img) * p.Nq + q0 + r) * p.ldo + head * p.d;
 #pragma unroll
         for (int c = 0; c < DPAD; c += 16) {
@@ -327,8 +331,8 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 using namespace ctrl;
 
 extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt,
-                                     int nk_pad, void* out, long long ldo, int batch, int heads, int nq, int nk,
-                                     int head_dim, void* stream_) {
+                                     int nk_pad, void* out, long long ldo, float* lse, int batch, int heads, int nq,
+                                     int nk, int head_dim, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!q || !k || !vt || !out) return CTRLORA_ERR_ARG;
     const int d = head_dim;
@@ -338,7 +342,7 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
     memset(&p, 0, sizeof(p));
     p.Nq = nq; p.Nk = nk; p.heads = heads; p.d = d; p.d16 = (d + 15) / 16 * 16; p.nkc = (d + 63) / 64;
     p.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
-    p.out = reinterpret_cast<__half*>(out); p.ldo = ldo;
+    p.out = reinterpret_cast<__half*>(out); p.ldo = ldo; p.lse = lse;
     const bool multi = nk > 256;
     if (multi && d > 80) return CTRLORA_ERR_UNSUPPORTED;  // d_head 160 with > 256 keys: not on the 512x512 path
     const int bkv = multi ? 128 : (nk <= 128 ? 128 : 256);

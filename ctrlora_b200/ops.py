@@ -215,14 +215,14 @@ def layernorm(x, gamma, beta, eps=1e-5):
     return y.view(x.shape)
 
 
-def attention(q, k, vt, batch, heads, nq, nk, head_dim, out=None):
+def attention(q, k, vt, batch, heads, nq, nk, head_dim, out=None, lse=None):
     """q [batch*nq, heads*d], k [batch*nk, heads*d], vt [batch, heads, d, nk_pad] (fp16) -> [batch*nq, heads*d]."""
     _require_cuda(q, k, vt)
     if out is None:
         out = torch.empty((batch * nq, heads * head_dim), device=q.device, dtype=torch.float16)
     _count(1)
     check(_lib.load().ctrlora_attention_f16(_dp(q), q.stride(0), _dp(k), k.stride(0), _dp(vt), vt.shape[-1], _dp(out),
-                                            out.stride(0), batch, heads, nq, nk, head_dim, _sp()),
+                                            out.stride(0), _dp(lse), batch, heads, nq, nk, head_dim, _sp()),
           "ctrlora_attention_f16")
     return out
 
@@ -461,3 +461,20 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-5, betas=(0.9, 0.
     check(_lib.load().ctrlora_adamw_f32(_dp(params), _dp(grads), _dp(exp_avg), _dp(exp_avg_sq), params.numel(), float(lr),
                                         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                         float(grad_scale), _sp()), "adamw")
+
+
+def attention_bwd(q, k, v, o, dout, lse, batch, heads, nq, nk, head_dim, dq=None, dk=None, dv=None):
+    """Backward of ops.attention.  q/o/dout [batch*nq, H*d], k/v natural [batch*nk, H*d] (fp16, row strides free),
+    lse fp32 [batch, H, nq] from the forward.  Returns (dq, dk, dv) fp16."""
+    _require_cuda(q, k, v, o, dout, lse)
+    c = heads * head_dim
+    dq = torch.empty((batch * nq, c), device=q.device, dtype=torch.float16) if dq is None else dq
+    dk = torch.empty((batch * nk, c), device=q.device, dtype=torch.float16) if dk is None else dk
+    dv = torch.empty((batch * nk, c), device=q.device, dtype=torch.float16) if dv is None else dv
+    delta = torch.empty(batch * heads * nq, device=q.device, dtype=torch.float32)
+    _count(3)
+    check(_lib.load().ctrlora_attention_bwd_f16(_dp(q), q.stride(0), _dp(k), k.stride(0), _dp(v), v.stride(0), _dp(o), o.stride(0),
+                                                _dp(dout), dout.stride(0), _dp(lse), _dp(delta), _dp(dq), dq.stride(0), _dp(dk),
+                                                dk.stride(0), _dp(dv), dv.stride(0), batch, heads, nq, nk, head_dim, _sp()),
+          "ctrlora_attention_bwd_f16")
+    return dq, dk, dv

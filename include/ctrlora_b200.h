@@ -107,7 +107,8 @@ int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, 
  * replaces CrossAttention.forward   ldm/modules/attention.py:163-194 (and MemoryEfficientCrossAttention :197-243).
  * q [batch, nq, heads*d] (row stride ldq), k [batch, nk, heads*d] (ldk), vt = V transposed [batch, heads, d, nk_pad]. */
 int ctrlora_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt, int nk_pad,
-                          void* out, long long ldo, int batch, int heads, int nq, int nk, int head_dim, void* stream);
+                          void* out, long long ldo, float* lse /* optional [batch, heads, nq], log2 domain */, int batch,
+                          int heads, int nq, int nk, int head_dim, void* stream);
 
 /* Module-boundary layout/dtype conversion (the reference's tensors are NCHW fp32). */
 int ctrlora_nchw_f32_to_nhwc_f16(const float* src, void* dst, int batch, int channels, int hw, int c_pad, void* stream);
@@ -145,6 +146,13 @@ int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_unco
  */
 int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b, long long ldb, int m, int p_dim, int q_dim, float* out,
                          long long ldo, float alpha, float beta, float* ws, long long ws_bytes, void* stream);
+
+/* Attention backward (autograd of ldm/modules/attention.py:163-194): v is the NATURAL [batch*nk, heads*d] layout; lse is
+ * what ctrlora_attention_f16 wrote; delta_ws: fp32 scratch [batch*heads*nq].  dq/dk/dv: fp16, same layouts as q/k/v. */
+int ctrlora_attention_bwd_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                              const void* o, long long ldo, const void* dout, long long lddo, const float* lse,
+                              float* delta_ws, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
+                              int batch, int heads, int nq, int nk, int head_dim, void* stream);
 
 /* GroupNorm(+SiLU) backward: same source description as the forward (`args`, whose stats_ws is a scratch buffer for the
  * backward statistics); fwd_stats = the {sum, sumsq} buffer the forward left in ITS stats_ws.  dx1 / dx2: gradients of

@@ -137,3 +137,31 @@ def test_mse_loss_and_adamw():
         opt.step()
         ops.adamw_step(p, g, m, v, step, lr=1e-2)
     assert (p - p_ref.detach()).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 512, 512, 40), (1, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (2, 8, 256, 77, 40),
+                                         (2, 4, 200, 300, 16), (1, 8, 64, 64, 160), (2, 8, 1024, 77, 80), (1, 4, 130, 129, 32)])
+def test_attention_backward(B, H, Nq, Nk, d):
+    """dQ, dK, dV of the fused attention against torch autograd on the same fp16-rounded inputs."""
+    from ctrlora_b200 import ops
+    torch.manual_seed(6)
+    q, k, v = _rand(B * Nq, H * d), _rand(B * Nk, H * d), _rand(B * Nk, H * d)
+    dout = _rand(B * Nq, H * d)
+    nk_pad = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, H, d, nk_pad, device="cuda", dtype=torch.float16)
+    vt[..., :Nk] = v.view(B, Nk, H, d).permute(0, 2, 3, 1)
+    lse = torch.empty(B, H, Nq, device="cuda", dtype=torch.float32)
+    o = ops.attention(q, k, vt, B, H, Nq, Nk, d, lse=lse)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, dout, lse, B, H, Nq, Nk, d)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = qf.view(B, Nq, H, d).permute(0, 2, 1, 3)
+    kh = kf.view(B, Nk, H, d).permute(0, 2, 1, 3)
+    vh = vf.view(B, Nk, H, d).permute(0, 2, 1, 3)
+    sim = (qh @ kh.transpose(-1, -2)) * d ** -0.5
+    ref = (sim.softmax(-1) @ vh).permute(0, 2, 1, 3).reshape(B * Nq, H * d)
+    lse_ref = torch.logsumexp(sim, -1) * 1.4426950408889634
+    _close(lse, lse_ref, 1e-3)
+    ref.backward(dout.float())
+    _close(dq, qf.grad, 5e-3)
+    _close(dk, kf.grad, 5e-3)
+    _close(dv, vf.grad, 5e-3)
