@@ -25,6 +25,7 @@ class GemmArgs(C.Structure):
         ("head_dim", c_int), ("tok_pad", c_int), ("bf16", c_int),
         ("split_k", c_int), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_ll),
         ("splitk_counters", c_void_p), ("splitk_counters_len", c_int),
+        ("dup_out", c_void_p), ("dup_ld", c_int),
     ]
 
 
@@ -78,10 +79,11 @@ _ARGTYPES = {
     "ctrlora_upsample2x_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_im2col_s2_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_cast_transpose_f32_to_f16": [_P, _P, _L, _I, _I, _P],
+    "ctrlora_transpose_f16": [_P, _P, _L, _I, _I, _P],
     "ctrlora_ddim_update": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P],
     "ctrlora_wgrad_tn_f16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _F, _F, _P, _L, _P],
-    "ctrlora_groupnorm_bwd_f16": [_P, _P, _P, _P, _L, _F, _P, _L, _F, _P, _P, _P],
-    "ctrlora_layernorm_bwd_f16": [_P, _L, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P],
+    "ctrlora_groupnorm_bwd_f16": [_P, _P, _P, _P, _L, _F, _P, _L, _F, _P, _L, _P, _P, _P],
+    "ctrlora_layernorm_bwd_f16": [_P, _L, _P, _L, _P, _L, _I, _I, _P, _F, _P, _P, _P, _L, _P],
     "ctrlora_geglu_fwd_f16": [_P, _P, _L, _I, _P],
     "ctrlora_geglu_bwd_f16": [_P, _P, _P, _L, _I, _P],
     "ctrlora_colsum": [_P, _I, _L, _L, _I, _F, _P, _P],
@@ -125,6 +127,7 @@ EXPORTS = [
     "ctrlora_upsample2x_f16",
     "ctrlora_im2col_s2_f16",
     "ctrlora_cast_transpose_f32_to_f16",
+    "ctrlora_transpose_f16",
     "ctrlora_ddim_update",
     "ctrlora_wgrad_tn_f16",
     "ctrlora_attention_bwd_f16",

@@ -135,6 +135,17 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, __half* __r
     dst[i] = __float2half_rn(src[(b * R + r) * C + c]);
 }
 
+// ---- fp16 [batch, R, C] -> fp16 [batch, C, R]  (transposed kernel copies of weights for the dgrad GEMMs)
+__global__ void transpose_f16_kernel(const __half* __restrict__ src, __half* __restrict__ dst, long long batch, int R, int C) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = batch * R * C;
+    if (i >= total) return;
+    const int r = static_cast<int>(i % R);
+    const int c = static_cast<int>((i / R) % C);
+    const long long b = i / (static_cast<long long>(R) * C);
+    dst[i] = src[(b * R + r) * C + c];
+}
+
 // ---- DDIM update, one pass: CFG combine + pred_x0 + x_prev; explicit round-to-nearest ops in the reference's
 // order (cldm/ddim_hacked.py:192,215,226-230) so that no FMA contraction changes the fp32 results.
 // stats[b] += sum(x_prev^2) of image b (warp-reduced), a per-step scalar the host can read back.
@@ -239,6 +250,14 @@ extern "C" int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, lo
     const long long total = batch * rows * cols;
     cast_transpose_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__half*>(dst), batch,
                                                                             rows, cols);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_transpose_f16(const void* src, void* dst, long long batch, int rows, int cols, void* stream) {
+    if (!src || !dst) return CTRLORA_ERR_ARG;
+    const long long total = batch * rows * cols;
+    transpose_f16_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __half*>(src),
+                                                                           reinterpret_cast<__half*>(dst), batch, rows, cols);
     return LAUNCH_OK();
 }
 

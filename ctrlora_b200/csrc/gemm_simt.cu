@@ -49,6 +49,7 @@ __global__ void gemm_simt_kernel(ctrlora_gemm_args a, int M, int rows_per_img) {
     if (a.transposed[seg]) {
         reinterpret_cast<__half*>(a.out[seg])[(static_cast<long long>(img) * a.seg_width + nloc) * a.tok_pad + tok] =
             __float2half_rn(v);
+        if (a.dup_out) reinterpret_cast<__half*>(a.dup_out)[m * a.dup_ld + nloc] = __float2half_rn(v);
     } else if (a.out_f32) {
         reinterpret_cast<float*>(a.out[seg])[m * a.ldc + nloc] = v;
     } else {

@@ -96,6 +96,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, c
         __half* o = reinterpret_cast<__half*>(p.out[seg]) + (static_cast<long long>(img) * p.seg_width + nloc) * p.tok_pad + tok;
         for (int j = 0; j < 32; ++j)
             if (c + j < bn_out && nbase + j < p.N) o[static_cast<long long>(j) * p.tok_pad] = __float2half_rn(v[j]);
+        if (p.dup_out) {
+            __half* o2 = p.dup_out + m * p.dup_ld + nloc;
+            for (int j = 0; j < 32; ++j)
+                if (c + j < bn_out && nbase + j < p.N) o2[j] = __float2half_rn(v[j]);
+        }
     } else if (p.out_f32) {
         float* o = reinterpret_cast<float*>(p.out[seg]) + m * p.ldc + nloc;
         if (full_chunk && (p.ldc & 3) == 0) {
@@ -534,6 +539,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     p.rowbias_ld = a->rowbias_ld > 0 ? a->rowbias_ld : a->n;
     p.out_scale = a->out_scale;
     p.head_dim = a->head_dim; p.tok_pad = a->tok_pad;
+    p.dup_out = reinterpret_cast<__half*>(a->dup_out); p.dup_ld = a->dup_ld;
 
     CUtensorMap tmA, tmB, tmA2, tmB2;
     {

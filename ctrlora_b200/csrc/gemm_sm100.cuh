@@ -45,6 +45,8 @@ struct GemmKParams {
     int ldr;
     float out_scale;
     int head_dim, tok_pad;
+    __half* dup_out;               // transposed segments are ALSO stored row-major here (training keeps natural V)
+    int dup_ld;
     int bf16;
 };
 

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(512)
 gn_bwd_apply_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int groups, int pix_per_block,
                     const float* __restrict__ fstats, const float* __restrict__ bstats, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, int silu, __half* __restrict__ dx1, long long ldd1, float scale1,
-                    __half* __restrict__ dx2, long long ldd2, float scale2) {
+                    __half* __restrict__ dx2, long long ldd2, float scale2, const __half* __restrict__ res, long long ldres) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;
@@ -364,8 +364,16 @@ gn_bwd_apply_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int g
         for (int e = 0; e < 8; ++e) {
             const float xh = (x[e] - mu[e]) * rs[e];
             const float dz = silu ? d[e] * dsilu_f(xh * ga[e] + be[e]) : d[e];
-            o[e] = osc * rs[e] * (dz * ga[e] - m1[e] - xh * m2[e]);
+            o[e] = rs[e] * (dz * ga[e] - m1[e] - xh * m2[e]);
         }
+        if (res) {  // gradient arriving over the block's skip path (identity residual or the 1x1 skip conv's dgrad)
+            float rr[8];
+            load8h(res + pix * ldres + vec * 8, rr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += rr[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] *= osc;
 #pragma unroll
         for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
         *reinterpret_cast<uint4*>(dst + pix * ldd + coff) = u;
@@ -377,7 +385,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __half* __restrict__ x, long long ldx, const __half* __restrict__ dy, long long ldy,
                      __half* __restrict__ dx, long long lddx, int M, int C, const float* __restrict__ gamma, float eps,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, const __half* __restrict__ res, long long ldres) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float sm[];  // [2][C] when dgamma
@@ -435,12 +443,14 @@ layernorm_bwd_kernel(const __half* __restrict__ x, long long ldx, const __half* 
         for (int i = 0; i < MAXV; ++i) {
             const int vi = lane + i * 32;
             if (vi < vecs) {
+                float rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (res) load8h(res + row * ldres + vi * 8, rr);  // gradient of the residual branch
                 uint4 u;
                 __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    h[e] = __floats2half2_rn(rstd * (d[i][2 * e] - s1 - v[i][2 * e] * s2),
-                                             rstd * (d[i][2 * e + 1] - s1 - v[i][2 * e + 1] * s2));
+                    h[e] = __floats2half2_rn(rstd * (d[i][2 * e] - s1 - v[i][2 * e] * s2) + rr[2 * e],
+                                             rstd * (d[i][2 * e + 1] - s1 - v[i][2 * e + 1] * s2) + rr[2 * e + 1]);
                 *reinterpret_cast<uint4*>(dx + row * lddx + vi * 8) = u;
             }
         }
@@ -464,7 +474,7 @@ layernorm_bwd_kernel(const __half* __restrict__ x, long long ldx, const __half* 
 
 extern "C" int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* a, const void* dy, const void* fwd_stats, void* dx1,
                                          long long ldd1, float dx1_scale, void* dx2, long long ldd2, float dx2_scale,
-                                         float* dgamma, float* dbeta, void* stream_) {
+                                         const void* res, long long ldres, float* dgamma, float* dbeta, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!a || !a->x1 || !dy || !fwd_stats || !a->stats_ws || !a->gamma || !a->beta) return CTRLORA_ERR_ARG;
     const int C = a->c1 + (a->x2 ? a->c2 : 0);
@@ -490,13 +500,13 @@ extern "C" int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* a, const 
     launch_pdl(gn_bwd_apply_kernel, grid, dim3(threads), (size_t)0, stream, s, reinterpret_cast<const __half*>(dy), C, HW,
                (int)a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), reinterpret_cast<const float*>(a->stats_ws),
                a->gamma, a->beta, a->eps, (int)a->silu, reinterpret_cast<__half*>(dx1), ldd1, dx1_scale,
-               reinterpret_cast<__half*>(dx2), ldd2, dx2_scale);
+               reinterpret_cast<__half*>(dx2), ldd2, dx2_scale, reinterpret_cast<const __half*>(res), ldres);
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
 
 extern "C" int ctrlora_layernorm_bwd_f16(const void* x, long long ldx, const void* dy, long long ldy, void* dx, long long lddx,
                                          int rows, int cols, const float* gamma, float eps, float* dgamma, float* dbeta,
-                                         void* stream_) {
+                                         const void* res, long long ldres, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (!x || !dy || !dx || !gamma || cols % 8 != 0 || cols > 1280 || (dgamma && !dbeta)) return CTRLORA_ERR_ARG;
     int grid = (rows + 7) / 8;
@@ -505,9 +515,10 @@ extern "C" int ctrlora_layernorm_bwd_f16(const void* x, long long ldx, const voi
     const __half* xp = reinterpret_cast<const __half*>(x);
     const __half* dp = reinterpret_cast<const __half*>(dy);
     __half* op = reinterpret_cast<__half*>(dx);
+    const __half* rp = reinterpret_cast<const __half*>(res);
     if (cols <= 512)
-        launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta);
+        launch_pdl(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta, rp, ldres);
     else
-        launch_pdl(layernorm_bwd_kernel<5>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta);
+        launch_pdl(layernorm_bwd_kernel<5>, dim3(grid), dim3(256), sm, stream, xp, ldx, dp, ldy, op, lddx, rows, cols, gamma, eps, dgamma, dbeta, rp, ldres);
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }

@@ -94,7 +94,7 @@ def _as_bhwc(a):
 def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0, residual=None, out_scale=1.0, a2=None,
          w2=None,
          geglu=False, out=None, out_f32=False, seg_outs=None, seg_width=0, transposed=(0, 0, 0), head_dim=0,
-         tok_pad=0, block_n=0, split_k=0, simt=False):
+         tok_pad=0, block_n=0, split_k=0, dup_out=None, simt=False):
     """out = epilogue(conv_or_linear(a, w) [+ a2 @ w2^T]); see `ctrlora_gemm_f16` in include/ctrlora_b200.h.
 
     a: fp16 [B,H,W,C] or [M,K]; w: fp16 [N(2N), ksize*ksize, C]; returns the output tensor ([..., N]).
@@ -144,6 +144,8 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
     ws, cnt = _splitk_buffers(a.device)
     args.split_k, args.splitk_ws, args.splitk_ws_bytes = split_k, ws.data_ptr(), SPLITK_WS_BYTES
     args.splitk_counters, args.splitk_counters_len = cnt.data_ptr(), SPLITK_COUNTERS
+    if dup_out is not None:
+        args.dup_out, args.dup_ld = dup_out.data_ptr(), dup_out.stride(0)
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
     _count()
@@ -356,7 +358,7 @@ def _gn_args(x1, gamma, beta, eps, silu, add1, add1_scale, x2, add2, add2_scale,
 
 
 def groupnorm_bwd(dy, fwd_stats, x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None,
-                  add2_scale=1.0, groups=32, want_dx2=False, dx2_scale=1.0, dgamma=None, dbeta=None):
+                  add2_scale=1.0, groups=32, want_dx2=False, dx2_scale=1.0, dgamma=None, dbeta=None, res=None, dx1_scale=1.0):
     """Backward of ops.groupnorm (same source description).  Returns dx1 (and dx2 scaled by dx2_scale if want_dx2);
     dgamma/dbeta (fp32 [C]) are accumulated into when given."""
     _require_cuda(dy, x1)
@@ -366,19 +368,23 @@ def groupnorm_bwd(dy, fwd_stats, x1, gamma, beta, eps, silu, *, add1=None, add1_
     dx1 = torch.empty((b, h, w, c1), device=dy.device, dtype=torch.float16)
     dx2 = torch.empty((b, h, w, c2), device=dy.device, dtype=torch.float16) if (want_dx2 and c2) else None
     _count(2)
-    check(_lib.load().ctrlora_groupnorm_bwd_f16(C.addressof(a), _dp(dy), _dp(fwd_stats), _dp(dx1), c1, 1.0, _dp(dx2), c2,
-                                                float(dx2_scale), _dp(dgamma), _dp(dbeta), _sp()), "groupnorm_bwd")
+    if res is not None:
+        assert res.dtype == torch.float16 and res.stride(-1) == 1 and res.shape[-1] == c1 + c2
+    check(_lib.load().ctrlora_groupnorm_bwd_f16(C.addressof(a), _dp(dy), _dp(fwd_stats), _dp(dx1), c1, float(dx1_scale), _dp(dx2), c2,
+                                                float(dx2_scale), _dp(res), res.stride(-2) if res is not None else 0,
+                                                _dp(dgamma), _dp(dbeta), _sp()), "groupnorm_bwd")
     return (dx1, dx2) if want_dx2 else dx1
 
 
-def layernorm_bwd(x, dy, gamma, eps=1e-5, dgamma=None, dbeta=None):
+def layernorm_bwd(x, dy, gamma, eps=1e-5, dgamma=None, dbeta=None, res=None):
     _require_cuda(x, dy)
     cols = x.shape[-1]
     x2, d2 = x.reshape(-1, cols), dy.reshape(-1, cols)
     dx = torch.empty((x2.shape[0], cols), device=x.device, dtype=torch.float16)
     _count()
     check(_lib.load().ctrlora_layernorm_bwd_f16(_dp(x2), x2.stride(0), _dp(d2), d2.stride(0), _dp(dx), cols, x2.shape[0],
-                                                cols, _dp(gamma), float(eps), _dp(dgamma), _dp(dbeta), _sp()), "layernorm_bwd")
+                                                cols, _dp(gamma), float(eps), _dp(dgamma), _dp(dbeta), _dp(res),
+                                                res.reshape(-1, cols).stride(0) if res is not None else 0, _sp()), "layernorm_bwd")
     return dx.view(x.shape)
 
 
@@ -478,3 +484,13 @@ def attention_bwd(q, k, v, o, dout, lse, batch, heads, nq, nk, head_dim, dq=None
                                                 dk.stride(0), _dp(dv), dv.stride(0), batch, heads, nq, nk, head_dim, _sp()),
           "ctrlora_attention_bwd_f16")
     return dq, dk, dv
+
+
+def transpose_f16(src, batch, rows, cols):
+    """fp16 [batch, rows, cols] -> fp16 [batch, cols, rows]"""
+    _require_cuda(src)
+    assert src.dtype == torch.float16 and src.is_contiguous() and src.numel() == batch * rows * cols
+    out = torch.empty((batch, cols, rows), device=src.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_transpose_f16(_dp(src), _dp(out), batch, rows, cols, _sp()), "transpose_f16")
+    return out

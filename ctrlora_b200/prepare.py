@@ -9,8 +9,19 @@ import torch
 from . import ops
 
 
+# Bumped by the trainer after every optimizer step: its fused AdamW kernel updates the flat parameter buffer behind
+# torch's back, so `_version` does not move for parameters tagged `_ctrlora_trainable`.
+TRAIN_VERSION = 0
+
+
+def bump_train_version():
+    global TRAIN_VERSION
+    TRAIN_VERSION += 1
+
+
 def _ver(*params):
-    return tuple((p.data_ptr(), p._version, tuple(p.shape)) if p is not None else None for p in params)
+    return tuple((p.data_ptr(), p._version, tuple(p.shape), TRAIN_VERSION if getattr(p, "_ctrlora_trainable", False) else 0)
+                 if p is not None else None for p in params)
 
 
 class PrepCache:
@@ -115,3 +126,15 @@ def effective(module):
 def lora_key(*linears):
     """cache-key component identifying which LoRA set is attached (switch_lora re-points `lora_layer`)"""
     return tuple(id(getattr(lin, "lora_layer", None)) for lin in linears)
+
+
+def weight_T(w16):
+    """fp16 kernel weight [N, 1, K] -> its transpose [K, 1, N] (dx = dy @ W uses the GEMM with this as the weight)."""
+    n, _, k = w16.shape
+    return ops.transpose_f16(w16.view(1, n, k).contiguous(), 1, n, k).view(k, 1, n)
+
+
+def conv_dgrad_weight(w16):
+    """fp16 conv kernel weight [Cout, taps, Cin] -> data-gradient weight [Cin, taps (flipped), Cout]:
+    dx = conv(dy, W_d) with the same 'same' padding."""
+    return w16.flip(1).permute(2, 1, 0).contiguous()

@@ -1,0 +1,562 @@
+"""CtrLoRA finetune training step on the sm_100a kernels: forward with saved activations, hand-scheduled backward,
+flat-buffer NCCL all-reduce of the trainable gradients and fused AdamW.
+
+reference call stack: LatentDiffusion.p_losses (ldm/models/diffusion/ddpm.py:885-920) ->
+ControlFinetuneLDM.apply_model (cldm/cldm_ctrlora_finetune.py:67-82) -> autograd backward -> DDP all-reduce ->
+AdamW over {lora_layer.*, zero_convs.*, middle_block_out.*, *norm*} (cldm_ctrlora_finetune.py:84-108).
+
+What is computed: the reference back-propagates weight gradients for every requires_grad parameter it
+reaches (385 M ControlNet + UNet decoder weights it never uses).  Here only what the optimizer's parameter set needs:
+  * activation gradients through the UNet decoder (frozen) -> the 13 control residuals,
+  * activation gradients through the ControlNet,
+  * weight gradients for LoRA down/up (factored: dUp = dY^T (X Down^T), dDown = (dY Up)^T X), zero-convs, and the
+    'norm'-named GroupNorm / LayerNorm affine parameters.
+The reference's activation checkpointing (util.py:102-151) is replaced by simply keeping the activations (180 GB HBM).
+The M = batch time-embedding MLP (time_embed, emb_layers: 12 tiny LoRA linears) is differentiated with torch fp32
+matmuls on [B, 1280] tensors -- negligible work, documented in DESIGN.md.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, prepare
+from .runtime import nchw_view, pixel_major, to_f16_rows
+
+f32 = prepare.bias_f32
+
+
+# ------------------------------------------------------------------------------------------------ gradient sink
+class GradSink:
+    """Flat fp32 buffers (params, grads, Adam moments) over the optimizer's parameter set, in the reference's order."""
+
+    def __init__(self, control_model):
+        from cldm.cldm_ctrlora_finetune import trainable_parameters
+        named = trainable_parameters(control_model)
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros_like(self.flat_g)
+        self.exp_avg_sq = torch.zeros_like(self.flat_g)
+        self._grad = {}
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + n].view(p.shape)  # the module now reads the flat buffer
+            p._ctrlora_trainable = True
+            self._grad[id(p)] = self.flat_g[off:off + n].view(p.shape)
+            off += n
+        self.numel = total
+
+    def grad(self, param):
+        """fp32 gradient view of a trainable parameter, or None if the optimizer does not own it."""
+        return self._grad.get(id(param)) if param is not None else None
+
+    def named_grads(self):
+        return {n: self._grad[id(p)] for n, p in zip(self.names, self.params)}
+
+    def zero(self):
+        self.flat_g.zero_()
+
+
+# ------------------------------------------------------------------------------------------------ weights
+def _cache(mod):
+    c = mod.__dict__.get("_tprep")
+    if c is None:
+        c = mod.__dict__["_tprep"] = prepare.PrepCache()
+    return c
+
+
+def lin_w(lin):
+    return _cache(lin).get(("w", prepare.lora_key(lin)), prepare.linear_params(lin), lambda: prepare.effective_linear_weight(lin))
+
+
+def lin_wT(lin):
+    return _cache(lin).get(("wT", prepare.lora_key(lin)), prepare.linear_params(lin), lambda: prepare.weight_T(lin_w(lin)))
+
+
+def cat_w(owner, key, lins):
+    params = [p for l in lins for p in prepare.linear_params(l)]
+    return _cache(owner).get((key, prepare.lora_key(*lins)), params, lambda: torch.cat([lin_w(l) for l in lins], 0).contiguous())
+
+
+def cat_wT(owner, key, lins):
+    params = [p for l in lins for p in prepare.linear_params(l)]
+    return _cache(owner).get((key + "T", prepare.lora_key(*lins)), params, lambda: prepare.weight_T(cat_w(owner, key, lins)))
+
+
+def conv_w(conv):
+    return _cache(conv).get("w", [conv.weight], lambda: prepare.conv_weight(conv.weight))
+
+
+def conv_wd(conv):
+    """data-gradient weight of a 'same' conv ([Cin, taps flipped, Cout]); for 1x1 convs it is the transpose"""
+    return _cache(conv).get("wd", [conv.weight], lambda: prepare.conv_dgrad_weight(conv_w(conv)))
+
+
+def lora_grads(lin, x2d, dy2d, G):
+    """Accumulate dUp, dDown of a LoRACompatibleLinear (y = x W^T + up(down(x))): cldm/lora.py:70-80,285-291."""
+    if G is None:
+        return
+    lora = getattr(lin, "lora_layer", None)
+    if lora is None:
+        return
+    g_up, g_down = G.grad(lora.up.weight), G.grad(lora.down.weight)
+    if g_up is None:
+        return
+    scale = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
+    r, k = lora.down.weight.shape
+    n = lora.up.weight.shape[0]
+    c = _cache(lora)
+    d16 = c.get("d16", [lora.down.weight], lambda: prepare.linear_weight(lora.down.weight))           # [r, 1, K]
+    u16t = c.get("u16t", [lora.up.weight], lambda: ops.cast_transpose(f32(lora.up.weight), 1, n, r).view(r, 1, n))  # [r, 1, N]
+    t1 = ops.gemm(x2d, d16)        # X Down^T   [M, r]
+    ops.wgrad_tn(dy2d, t1, out=g_up, alpha=scale, beta=1.0)
+    t2 = ops.gemm(dy2d, u16t)      # dY Up      [M, r]
+    ops.wgrad_tn(t2, x2d, out=g_down, alpha=scale, beta=1.0)
+
+
+# ------------------------------------------------------------------------------------------------ transformer block
+def tblock_fwd(blk, x2d, batch, n, ctx2d, nk):
+    dev = x2d.device
+    h16 = torch.float16
+    a1m, a2m, ff = blk.attn1, blk.attn2, blk.ff
+    inner = a1m.to_q.out_features
+    heads, d = a1m.heads, inner // a1m.heads
+    s = {"x": x2d, "batch": batch, "n": n, "nk": nk, "ctx": ctx2d}
+    ln = lambda norm, t: ops.layernorm(t, f32(prepare.effective(norm).weight), f32(prepare.effective(norm).bias), norm.eps)
+    # ---- self attention
+    s["n1"] = n1 = ln(blk.norm1, x2d)
+    np1 = (n + 7) // 8 * 8
+    q = torch.empty((batch * n, inner), device=dev, dtype=h16)
+    k, v = torch.empty_like(q), torch.empty_like(q)
+    vt = torch.empty((batch, heads, d, np1), device=dev, dtype=h16)
+    ops.gemm(n1, cat_w(a1m, "qkv", [a1m.to_q, a1m.to_k, a1m.to_v]), seg_outs=[q, k, vt], seg_width=inner, transposed=(0, 0, 1),
+             rows_per_img=n, head_dim=d, tok_pad=np1, dup_out=v)
+    s["lse1"] = torch.empty((batch, heads, n), device=dev, dtype=torch.float32)
+    s["q1"], s["k1"], s["v1"] = q, k, v
+    s["a1"] = ops.attention(q, k, vt, batch, heads, n, n, d, lse=s["lse1"])
+    o1 = a1m.to_out[0]
+    s["x1"] = x1 = ops.gemm(s["a1"], lin_w(o1), bias=f32(o1.bias), residual=x2d)
+    # ---- cross attention
+    s["n2"] = n2 = ln(blk.norm2, x1)
+    npk = (nk + 7) // 8 * 8
+    s["q2"] = ops.gemm(n2, lin_w(a2m.to_q))
+    k2 = torch.empty((batch * nk, inner), device=dev, dtype=h16)
+    v2 = torch.empty_like(k2)
+    vt2 = torch.empty((batch, heads, d, npk), device=dev, dtype=h16)
+    ops.gemm(ctx2d, cat_w(a2m, "kv", [a2m.to_k, a2m.to_v]), seg_outs=[k2, vt2], seg_width=inner, transposed=(0, 1, 0),
+             rows_per_img=nk, head_dim=d, tok_pad=npk, dup_out=v2)
+    s["k2"], s["v2"] = k2, v2
+    s["lse2"] = torch.empty((batch, heads, n), device=dev, dtype=torch.float32)
+    s["a2"] = ops.attention(s["q2"], k2, vt2, batch, heads, n, nk, d, lse=s["lse2"])
+    o2 = a2m.to_out[0]
+    s["x2"] = x2 = ops.gemm(s["a2"], lin_w(o2), bias=f32(o2.bias), residual=x1)
+    # ---- feed forward (GEGLU pre-activations are kept for the backward)
+    s["n3"] = n3 = ln(blk.norm3, x2)
+    proj, out = ff.net[0].proj, ff.net[2]
+    s["h"] = h = ops.gemm(n3, lin_w(proj), bias=f32(proj.bias))
+    s["g"] = g = ops.geglu_fwd(h)
+    x3 = ops.gemm(g, lin_w(out), bias=f32(out.bias), residual=x2)
+    return x3, s
+
+
+def tblock_bwd(blk, s, d_x3, G):
+    a1m, a2m, ff = blk.attn1, blk.attn2, blk.ff
+    inner = a1m.to_q.out_features
+    heads, d = a1m.heads, inner // a1m.heads
+    batch, n, nk, ctx2d = s["batch"], s["n"], s["nk"], s["ctx"]
+
+    def ln_bwd(norm, x, dy, res):
+        m = prepare.effective(norm)
+        gw, gb = (G.grad(m.weight), G.grad(m.bias)) if G is not None else (None, None)
+        return ops.layernorm_bwd(x, dy, f32(m.weight), norm.eps, gw, gb, res=res)
+
+    proj, out = ff.net[0].proj, ff.net[2]
+    d_g = ops.gemm(d_x3, lin_wT(out))
+    lora_grads(out, s["g"], d_x3, G)
+    d_h = ops.geglu_bwd(s["h"], d_g)
+    d_n3 = ops.gemm(d_h, lin_wT(proj))
+    lora_grads(proj, s["n3"], d_h, G)
+    d_x2 = ln_bwd(blk.norm3, s["x2"], d_n3, d_x3)
+    # ---- cross attention
+    o2 = a2m.to_out[0]
+    d_a2 = ops.gemm(d_x2, lin_wT(o2))
+    lora_grads(o2, s["a2"], d_x2, G)
+    dq2, dk2, dv2 = ops.attention_bwd(s["q2"], s["k2"], s["v2"], s["a2"], d_a2, s["lse2"], batch, heads, n, nk, d)
+    d_n2 = ops.gemm(dq2, lin_wT(a2m.to_q))
+    lora_grads(a2m.to_q, s["n2"], dq2, G)
+    lora_grads(a2m.to_k, ctx2d, dk2, G)
+    lora_grads(a2m.to_v, ctx2d, dv2, G)
+    d_x1 = ln_bwd(blk.norm2, s["x1"], d_n2, d_x2)
+    # ---- self attention
+    o1 = a1m.to_out[0]
+    d_a1 = ops.gemm(d_x1, lin_wT(o1))
+    lora_grads(o1, s["a1"], d_x1, G)
+    dqkv = torch.empty((batch * n, 3 * inner), device=d_x3.device, dtype=torch.float16)
+    ops.attention_bwd(s["q1"], s["k1"], s["v1"], s["a1"], d_a1, s["lse1"], batch, heads, n, n, d, dq=dqkv[:, :inner],
+                      dk=dqkv[:, inner:2 * inner], dv=dqkv[:, 2 * inner:])
+    d_n1 = ops.gemm(dqkv, cat_wT(a1m, "qkv", [a1m.to_q, a1m.to_k, a1m.to_v]))
+    lora_grads(a1m.to_q, s["n1"], dqkv[:, :inner], G)
+    lora_grads(a1m.to_k, s["n1"], dqkv[:, inner:2 * inner], G)
+    lora_grads(a1m.to_v, s["n1"], dqkv[:, 2 * inner:], G)
+    return ln_bwd(blk.norm1, s["x"], d_n1, d_x1)
+
+
+# ------------------------------------------------------------------------------------------------ spatial transformer
+def st_fwd(st, x, ctx):
+    xp = pixel_major(x)
+    b, h, w, c = xp.shape
+    gn = prepare.effective(st.norm)
+    xn, stats = ops.groupnorm(xp, f32(gn.weight), f32(gn.bias), gn.eps, False, groups=gn.num_groups, want_stats=True)
+    y = ops.gemm(xn, conv_w(st.proj_in), bias=f32(st.proj_in.bias))
+    y2d = y.view(b * h * w, -1)
+    ctx2d, nk = to_f16_rows(ctx), ctx.shape[1]
+    blocks = []
+    for blk in st.transformer_blocks:
+        y2d, bs = tblock_fwd(blk, y2d, b, h * w, ctx2d, nk)
+        blocks.append(bs)
+    out = ops.gemm(y2d.view(b, h, w, -1), conv_w(st.proj_out), bias=f32(st.proj_out.bias), residual=xp.view(b * h * w, c))
+    return nchw_view(out), {"xp": xp, "stats": stats, "blocks": blocks, "shape": (b, h, w, c)}
+
+
+def st_bwd(st, s, d_out, G):
+    b, h, w, c = s["shape"]
+    dop = pixel_major(d_out)
+    d_y = ops.gemm(dop, conv_wd(st.proj_out)).view(b * h * w, -1)
+    for blk, bs in zip(reversed(st.transformer_blocks), reversed(s["blocks"])):
+        d_y = tblock_bwd(blk, bs, d_y, G)
+    d_xn = ops.gemm(d_y.view(b, h, w, -1), conv_wd(st.proj_in))
+    gn = prepare.effective(st.norm)
+    gw, gb = (G.grad(gn.weight), G.grad(gn.bias)) if G is not None else (None, None)
+    dx = ops.groupnorm_bwd(d_xn, s["stats"], s["xp"], f32(gn.weight), f32(gn.bias), gn.eps, False, groups=gn.num_groups,
+                           dgamma=gw, dbeta=gb, res=dop.view(b * h * w, c))
+    return nchw_view(dx)
+
+
+# ------------------------------------------------------------------------------------------------ res block
+def res_fwd(rb, x, rowbias):
+    """x: NCHW-view tensor or runtime.CatSpec; rowbias: fp32 [B, Cout] slice of the network's emb GEMV."""
+    from .runtime import CatSpec
+    gn1, conv1, gn2, conv2 = rb.in_layers[0], rb.in_layers[2], rb.out_layers[0], rb.out_layers[3]
+    skip = None if isinstance(rb.skip_connection, nn.Identity) else rb.skip_connection
+    s = {}
+    if isinstance(x, CatSpec):
+        src = dict(x1=pixel_major(x.x1), add1=None if x.add1 is None else pixel_major(x.add1), add1_scale=x.s1,
+                   x2=None if x.x2 is None else pixel_major(x.x2), add2=None if x.add2 is None else pixel_major(x.add2),
+                   add2_scale=x.s2)
+        a, xp, stats1 = ops.groupnorm(src["x1"], f32(gn1.weight), f32(gn1.bias), gn1.eps, True, add1=src["add1"],
+                                      add1_scale=x.s1, x2=src["x2"], add2=src["add2"], add2_scale=x.s2, want_raw=True,
+                                      want_stats=True)
+    else:
+        xp = pixel_major(x)
+        src = dict(x1=xp, add1=None, add1_scale=1.0, x2=None, add2=None, add2_scale=1.0)
+        a, stats1 = ops.groupnorm(xp, f32(gn1.weight), f32(gn1.bias), gn1.eps, True, want_stats=True)
+    b, h, w, cin = xp.shape
+    hmid = ops.gemm(a, conv_w(conv1), ksize=3, bias=f32(conv1.bias), rowbias=rowbias)
+    c, stats2 = ops.groupnorm(hmid, f32(gn2.weight), f32(gn2.bias), gn2.eps, True, want_stats=True)
+    if skip is not None:
+        wsk = _cache(skip).get("w2d", [skip.weight], lambda: prepare.conv_weight(skip.weight).view(rb.out_channels, cin))
+        bsum = _cache(rb).get("bsum", [conv2.bias, skip.bias], lambda: (conv2.bias.float() + skip.bias.float()).contiguous())
+        out = ops.gemm(c, conv_w(conv2), ksize=3, bias=bsum, a2=xp, w2=wsk)
+    else:
+        out = ops.gemm(c, conv_w(conv2), ksize=3, bias=f32(conv2.bias), residual=xp.view(b * h * w, cin))
+    s.update(src=src, stats1=stats1, hmid=hmid, stats2=stats2, shape=(b, h, w, cin))
+    return nchw_view(out), s
+
+
+def res_bwd(rb, s, d_out, rowbias_grad=None, want_dx2=False, dx1_scale=1.0):
+    """Returns dx1 (times dx1_scale) and, if want_dx2, the gradient of the second concat half times its add2_scale."""
+    gn1, conv1, gn2, conv2 = rb.in_layers[0], rb.in_layers[2], rb.out_layers[0], rb.out_layers[3]
+    skip = None if isinstance(rb.skip_connection, nn.Identity) else rb.skip_connection
+    b, h, w, cin = s["shape"]
+    dop = pixel_major(d_out)
+    d_c = ops.gemm(dop, conv_wd(conv2), ksize=3)
+    d_skip = ops.gemm(dop, conv_wd(skip)).view(b * h * w, cin) if skip is not None else dop.view(b * h * w, cin)
+    d_hmid = ops.groupnorm_bwd(d_c, s["stats2"], s["hmid"], f32(gn2.weight), f32(gn2.bias), gn2.eps, True)
+    if rowbias_grad is not None:
+        ops.image_colsum(d_hmid.view(b * h * w, -1), b, rowbias_grad)
+    d_a = ops.gemm(d_hmid, conv_wd(conv1), ksize=3)
+    src = s["src"]
+    res = ops.groupnorm_bwd(d_a, s["stats1"], src["x1"], f32(gn1.weight), f32(gn1.bias), gn1.eps, True, add1=src["add1"],
+                            add1_scale=src["add1_scale"], x2=src["x2"], add2=src["add2"], add2_scale=src["add2_scale"],
+                            want_dx2=want_dx2, dx2_scale=src["add2_scale"], res=d_skip, dx1_scale=dx1_scale)
+    if want_dx2:
+        return nchw_view(res[0]), nchw_view(res[1])
+    return nchw_view(res)
+
+
+# ------------------------------------------------------------------------------------------------ resampling
+def down_fwd(ds, x):
+    xp = pixel_major(x).contiguous()
+    b, h, w, c = xp.shape
+    col = ops.im2col_s2(xp)
+    wk = _cache(ds).get("w", [ds.op.weight], lambda: prepare.conv_weight(ds.op.weight).view(ds.out_channels, 1, 9 * c))
+    return nchw_view(ops.gemm(col, wk, bias=f32(ds.op.bias))), {"shape": (b, h, w, c)}
+
+
+def down_bwd(ds, s, d_out):
+    b, h, w, c = s["shape"]
+    wk = _cache(ds).get("w", [ds.op.weight], lambda: prepare.conv_weight(ds.op.weight).view(ds.out_channels, 1, 9 * c))
+    wt = _cache(ds).get("wT", [ds.op.weight], lambda: prepare.weight_T(wk))
+    d_col = ops.gemm(pixel_major(d_out), wt)  # [B, h/2, w/2, 9*C]
+    return nchw_view(ops.im2col_s2_bwd(d_col, h, w))
+
+
+def up_fwd(us, x):
+    up = ops.upsample2x(pixel_major(x).contiguous())
+    return nchw_view(ops.gemm(up, conv_w(us.conv), ksize=3, bias=f32(us.conv.bias))), {}
+
+
+def up_bwd(us, s, d_out):
+    d_up = ops.gemm(pixel_major(d_out), conv_wd(us.conv), ksize=3)
+    return nchw_view(ops.upsample2x_bwd(d_up))
+
+
+# ------------------------------------------------------------------------------------------------ block sequences
+def seq_fwd(seq, x, emb, ctx):
+    """TimestepEmbedSequential in training mode: returns (out, tape) with one (kind, module, saved) per child."""
+    from ldm.modules.attention import SpatialTransformer
+    from ldm.modules.diffusionmodules.openaimodel import Downsample, ResBlock, Upsample, _Conv
+    tape = []
+    for layer in seq:
+        if isinstance(layer, ResBlock):
+            x, s = res_fwd(layer, x, emb.slices[id(layer)])
+            tape.append(("res", layer, s))
+        elif isinstance(layer, SpatialTransformer):
+            x, s = st_fwd(layer, x, ctx)
+            tape.append(("st", layer, s))
+        elif isinstance(layer, Downsample):
+            x, s = down_fwd(layer, x)
+            tape.append(("down", layer, s))
+        elif isinstance(layer, Upsample):
+            x, s = up_fwd(layer, x)
+            tape.append(("up", layer, s))
+        elif isinstance(layer, _Conv):
+            x = layer(x)  # the 4-channel input conv: nothing upstream needs its gradient
+            tape.append(("stop", layer, None))
+        else:
+            raise NotImplementedError(type(layer))
+    return x, tape
+
+
+def seq_bwd(tape, d, G, emb_grads=None, first_res_kw=None):
+    """Backward through one block; returns the input gradient (or a tuple for a CatSpec-fed first ResBlock)."""
+    for i in range(len(tape) - 1, -1, -1):
+        kind, mod, s = tape[i]
+        if kind == "res":
+            kw = first_res_kw if (i == 0 and first_res_kw) else {}
+            rg = emb_grads.get(id(mod)) if emb_grads is not None else None
+            d = res_bwd(mod, s, d, rowbias_grad=rg, **kw)
+        elif kind == "st":
+            d = st_bwd(mod, s, d, G)
+        elif kind == "down":
+            d = down_bwd(mod, s, d)
+        elif kind == "up":
+            d = up_bwd(mod, s, d)
+        elif kind == "stop":
+            return None
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ time-embedding MLP
+def emb_mlp_backward(net, t_emb, emb, d_slices, G):
+    """Gradients of time_embed.{0,2} and every emb_layers.1 LoRA pair from the per-ResBlock d(rowbias) (fp32 [B, Cout]).
+    M = batch rows only: plain torch fp32 matmuls (cuBLAS) -- see the module docstring."""
+    from ldm.modules.diffusionmodules.openaimodel import ResBlock
+
+    def lora_lin_bwd(lin, x, dy):
+        lora = getattr(lin, "lora_layer", None)
+        w = lin.weight.detach().float()
+        if lora is not None:
+            dwn, up = lora.down.weight.detach().float(), lora.up.weight.detach().float()
+            sc = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
+            gu, gd = G.grad(lora.up.weight), G.grad(lora.down.weight)
+            if gu is not None:
+                gu.add_(sc * dy.t() @ (x @ dwn.t()))
+                gd.add_(sc * (dy @ up).t() @ x)
+            w = w + sc * up @ dwn
+        return dy @ w
+
+    se = torch.nn.functional.silu(emb)
+    d_se = torch.zeros_like(emb)
+    for rb in (m for m in net.modules() if isinstance(m, ResBlock)):
+        d_se += lora_lin_bwd(rb.emb_layers[1], se, d_slices[id(rb)])
+    sig = torch.sigmoid(emb)
+    d_emb = d_se * sig * (1 + emb * (1 - sig))
+    l0, l2 = net.time_embed[0], net.time_embed[2]
+    hid_pre = torch.nn.functional.linear(t_emb, prepare_f32_weight(l0), l0.bias.detach().float())
+    hid = torch.nn.functional.silu(hid_pre)
+    d_hid = lora_lin_bwd(l2, hid, d_emb)
+    s0 = torch.sigmoid(hid_pre)
+    lora_lin_bwd(l0, t_emb, d_hid * s0 * (1 + hid_pre * (1 - s0)))
+
+
+def prepare_f32_weight(lin):
+    lora = getattr(lin, "lora_layer", None)
+    w = lin.weight.detach().float()
+    if lora is not None:
+        sc = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
+        w = w + sc * lora.up.weight.detach().float() @ lora.down.weight.detach().float()
+    return w
+
+
+# ------------------------------------------------------------------------------------------------ networks
+def controlnet_fwd(cn, hint, t, ctx):
+    emb = cn.embed(t)
+    ctx16 = to_f16_rows(ctx).view(ctx.shape[0], ctx.shape[1], -1)
+    tapes, hs, outs = [], [], []
+    h = hint
+    for module, zc in zip(cn.input_blocks, cn.zero_convs):
+        h, tape = seq_fwd(module, h, emb, ctx16)
+        tapes.append(tape)
+        hs.append(h)
+        outs.append(cn._zero_conv(zc, h))
+    h, tape = seq_fwd(cn.middle_block, h, emb, ctx16)
+    tapes.append(tape)
+    hs.append(h)
+    outs.append(cn._zero_conv(cn.middle_block_out, h))
+    return outs, {"tapes": tapes, "hs": hs, "emb": emb, "t": t}
+
+
+def zero_conv_bwd(seq, h, d_out, G, upstream):
+    """1x1 zero-conv: dW = dY^T H, db = colsum(dY), dH = dY W (+ the gradient arriving from the next block)."""
+    conv = prepare.effective(seq[0])
+    hp, dp = pixel_major(h), pixel_major(d_out)
+    b, hh, ww, c = hp.shape
+    h2d, d2d = hp.reshape(b * hh * ww, c), dp.reshape(b * hh * ww, c)
+    gw, gb = G.grad(conv.weight), G.grad(conv.bias)
+    if gw is not None:
+        ops.wgrad_tn(d2d, h2d, out=gw.view(c, c), beta=1.0)
+        ops.colsum(d2d, gb)
+    wt = _cache(conv).get("wT", [conv.weight], lambda: prepare.weight_T(prepare.conv_weight(conv.weight)))
+    up = None if upstream is None else pixel_major(upstream).reshape(b * hh * ww, c)
+    return nchw_view(ops.gemm(dp, wt, residual=up))
+
+
+def controlnet_bwd(cn, saved, d_outs, G):
+    from ldm.modules.diffusionmodules.openaimodel import ResBlock
+    emb = saved["emb"]
+    bsz = emb.raw.shape[0]
+    blocks = [m for m in cn.modules() if isinstance(m, ResBlock)]
+    d_all = torch.zeros((bsz, sum(b.out_channels for b in blocks)), device=emb.raw.device, dtype=torch.float32)
+    emb_grads, off = {}, 0
+    for b in blocks:
+        emb_grads[id(b)] = d_all[:, off:off + b.out_channels]
+        off += b.out_channels
+    tapes, hs = saved["tapes"], saved["hs"]
+    d_h = zero_conv_bwd(cn.middle_block_out, hs[-1], d_outs[-1], G, None)
+    d_h = seq_bwd(tapes[-1], d_h, G, emb_grads)
+    for i in range(len(cn.input_blocks) - 1, -1, -1):
+        d_h = zero_conv_bwd(cn.zero_convs[i], hs[i], d_outs[i], G, d_h)
+        d_h = seq_bwd(tapes[i], d_h, G, emb_grads)
+    from ldm.modules.diffusionmodules.util import timestep_embedding
+    t_emb = timestep_embedding(saved["t"], cn.model_channels)
+    emb_mlp_backward(cn, t_emb, emb.raw, emb_grads, G)
+
+
+def unet_fwd(unet, x, t, ctx, control, scales, only_mid_control=False):
+    """ControlledUnetModel.forward (cldm/cldm.py:22-45) with the decoder taped; control: 13 tensors, scales: 13 floats."""
+    from .runtime import CatSpec
+    with torch.no_grad():
+        emb = unet.embed(t)
+        ctx16 = to_f16_rows(ctx).view(ctx.shape[0], ctx.shape[1], -1)
+        hs = []
+        h = x
+        for module in unet.input_blocks:
+            h = module(h, emb, ctx16)
+            hs.append(h)
+        h = unet.middle_block(h, emb, ctx16)
+    ctrl = list(zip(control, scales))
+    add_mid, s_mid = ctrl.pop()
+    tapes = []
+    for i, module in enumerate(unet.output_blocks):
+        skip = hs.pop()
+        add, sc = (None, 1.0) if only_mid_control else ctrl.pop()
+        spec = CatSpec(h, add1=add_mid if i == 0 else None, s1=s_mid, x2=skip, add2=add, s2=sc)
+        h, tape = seq_fwd(module, spec, emb, ctx16)
+        tapes.append(tape)
+    # out: GroupNorm32 -> SiLU -> conv3x3 (kept on the inference kernels, plus the saved statistics)
+    gn, conv = unet.out[0], unet.out[2]
+    hp = pixel_major(h)
+    a, stats = ops.groupnorm(hp, f32(gn.weight), f32(gn.bias), gn.eps, True, want_stats=True)
+    n_pad = (unet.out_channels + 15) // 16 * 16
+    bias = unet._prep.get("out_bias", [conv.bias], lambda: torch.cat(
+        [conv.bias.detach().float(), torch.zeros(n_pad - unet.out_channels, device=conv.bias.device)]).contiguous())
+    y = ops.gemm(a, conv.kernel_weight(pad_out=n_pad), ksize=3, bias=bias, out_f32=True)
+    eps = ops.nhwc_to_nchw_f32(y, unet.out_channels)
+    return eps, {"tapes": tapes, "hp": hp, "stats": stats, "n_pad": n_pad, "only_mid": only_mid_control}
+
+
+def unet_bwd(unet, saved, d_eps16):
+    """d_eps16: fp16 pixel-major [B,H,W,16] gradient of eps (first 4 channels live).  Returns the 13 control gradients
+    (already multiplied by their control_scales), in the ControlNet's output order."""
+    gn, conv = unet.out[0], unet.out[2]
+    wd = _cache(conv).get("wd_out", [conv.weight],
+                          lambda: prepare.conv_dgrad_weight(conv.kernel_weight(pad_out=saved["n_pad"])))  # [320, 9, 16]
+    d_a = ops.gemm(d_eps16, wd, ksize=3)
+    d_h = nchw_view(ops.groupnorm_bwd(d_a, saved["stats"], saved["hp"], f32(gn.weight), f32(gn.bias), gn.eps, True))
+    d_ctrl = []
+    tapes = saved["tapes"]
+    for i in range(len(tapes) - 1, -1, -1):
+        want2 = not saved["only_mid"]
+        if i == 0:
+            # x1 = h_mid (+ s_mid * c_mid): only the control half of that sum needs a gradient
+            src = tapes[0][0][2]["src"]
+            res = seq_bwd(tapes[0], d_h, None, None, first_res_kw=dict(want_dx2=want2, dx1_scale=src["add1_scale"]))
+        else:
+            res = seq_bwd(tapes[i], d_h, None, None, first_res_kw=dict(want_dx2=want2))
+        if want2:
+            d_h, d2 = res
+            d_ctrl.append(d2)
+        else:
+            d_h = res
+    # d_ctrl holds gradients for control[11], ..., control[0] in pop() order reversed: decoder block i consumed control[11 - i]
+    d_ctrl = d_ctrl[::-1] if d_ctrl else []  # now index j = decoder block j -> control[11 - j]
+    ordered = [None] * 13
+    for j, g in enumerate(d_ctrl):
+        ordered[11 - j] = g
+    ordered[12] = d_h  # scaled by s_mid inside the first decoder block's GroupNorm backward
+    return ordered
+
+
+# ------------------------------------------------------------------------------------------------ trainer
+class FinetuneTrainer:
+    """One data-parallel CtrLoRA finetune step per call (configs ctrlora_finetune_sd15_rank*.yaml)."""
+
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None):
+        self.model = model
+        self.cn = model.control_model
+        self.unet = model.model.diffusion_model
+        self.G = GradSink(self.cn)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.step_count = 0
+
+    def loss_and_grads(self, x0, hint_latent, context, t, noise):
+        """q_sample -> apply_model -> MSE -> backward into the flat gradient buffer.  Returns the loss (fp32 tensor)."""
+        m = self.model
+        self.G.zero()
+        x_noisy = m.q_sample(x_start=x0, t=t, noise=noise)
+        control, cn_saved = controlnet_fwd(self.cn, hint_latent, t, context)
+        eps, un_saved = unet_fwd(self.unet, x_noisy, t, context, control, m.control_scales, m.only_mid_control)
+        loss, d_eps = ops.mse_loss_grad(eps, noise, c_pad=un_saved["n_pad"])
+        d_ctrl = unet_bwd(self.unet, un_saved, d_eps)
+        if m.only_mid_control:
+            d_ctrl = [d if d is not None else torch.zeros_like(c) for d, c in zip(d_ctrl, control)]
+        controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G)
+        self.last_eps = eps
+        return loss
+
+    def step(self, x0, hint_latent, context, t, noise):
+        loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.G.flat_g, group=self.pg)  # one flat NCCL all-reduce over NVLink
+        self.step_count += 1
+        ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,
+                       betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)
+        prepare.bump_train_version()
+        return loss

@@ -73,6 +73,8 @@ typedef struct ctrlora_gemm_args {
     long long splitk_ws_bytes;
     unsigned int* splitk_counters;   /* arrival counters: all zero on entry, left all zero on exit */
     int splitk_counters_len;
+    void* dup_out;          /* optional: transposed segments are also stored row-major here (fp16, row stride dup_ld) */
+    int dup_ld;
 } ctrlora_gemm_args;
 
 int ctrlora_gemm_f16(const ctrlora_gemm_args* args, void* stream);
@@ -131,6 +133,9 @@ int ctrlora_im2col_s2_f16(const void* src, void* dst, int batch, int h, int w, i
 /* weight preparation: fp32 [batch, rows, cols] -> fp16 [batch, cols, rows] */
 int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, long long batch, int rows, int cols, void* stream);
 
+/* fp16 [batch, rows, cols] -> fp16 [batch, cols, rows] (transposed weight copies for the data-gradient GEMMs) */
+int ctrlora_transpose_f16(const void* src, void* dst, long long batch, int rows, int cols, void* stream);
+
 /* DDIM update in one pass   cldm/ddim_hacked.py:190-192 (CFG, e_uncond may be NULL), :208-231 (pred_x0, x_prev).
  * fp32, round-to-nearest ops in the reference's order. stats (optional, [batch]) receives sum(x_prev^2) per image. */
 int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise, float* x_prev,
@@ -159,11 +164,14 @@ int ctrlora_attention_bwd_f16(const void* q, long long ldq, const void* k, long 
  * the two concat halves (fp16, row strides ldd1 / ldd2, scaled by dx*_scale; dx2 may be NULL).  dgamma/dbeta (fp32 [C],
  * accumulated into) may be NULL. */
 int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* args, const void* dy, const void* fwd_stats, void* dx1,
-                              long long ldd1, float dx1_scale, void* dx2, long long ldd2, float dx2_scale, float* dgamma,
-                              float* dbeta, void* stream);
+                              long long ldd1, float dx1_scale, void* dx2, long long ldd2, float dx2_scale,
+                              const void* res /* optional fp16 [rows, ldres]: added to the concat gradient */, long long ldres,
+                              float* dgamma, float* dbeta, void* stream);
 /* LayerNorm backward (statistics recomputed from x); dgamma/dbeta accumulated into (may be NULL). */
 int ctrlora_layernorm_bwd_f16(const void* x, long long ldx, const void* dy, long long ldy, void* dx, long long lddx, int rows,
-                              int cols, const float* gamma, float eps, float* dgamma, float* dbeta, void* stream);
+                              int cols, const float* gamma, float eps, float* dgamma, float* dbeta,
+                              const void* res /* optional fp16 residual-branch gradient added to dx */, long long ldres,
+                              void* stream);
 /* GEGLU on the stored projection h = [value | gate] ([rows, 2n]): out = value * gelu(gate), and its backward. */
 int ctrlora_geglu_fwd_f16(const void* h, void* out, long long rows, int n, void* stream);
 int ctrlora_geglu_bwd_f16(const void* h, const void* dout, void* dh, long long rows, int n, void* stream);
