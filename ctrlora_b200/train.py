@@ -533,7 +533,9 @@ class FinetuneTrainer:
         self.G = GradSink(self.cn)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
         self.step_count = 0
 
     def loss_and_grads(self, x0, hint_latent, context, t, noise):
@@ -551,10 +553,16 @@ class FinetuneTrainer:
         self.last_eps = eps
         return loss
 
+    def reduce_gradients(self):
+        """The path's single exchange step: ONE all-reduce (SUM) of the flat trainable-gradient buffer (36.9 M fp32
+        elements for rank 128 = 148 MB; the reference's DDP reduces ~10x more).  The 1/world factor is
+        folded into the AdamW kernel."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.G.flat_g, group=self.pg)
+
     def step(self, x0, hint_latent, context, t, noise):
         loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.G.flat_g, group=self.pg)  # one flat NCCL all-reduce over NVLink
+        self.reduce_gradients()
         self.step_count += 1
         ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,
                        betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)

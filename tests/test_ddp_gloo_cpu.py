@@ -1,0 +1,64 @@
+"""N > 1 host logic on CPU (gloo, world_size 2): the flat trainable-gradient buffer, its single all-reduce and the
+replica consistency of the parameter set.  No kernels run here (they need sm_100a); the GPU-side arithmetic is covered
+by tests/test_train_gpu.py."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctrlora_b200 import dropin
+        dropin.activate()
+        from cldm.model import create_model
+        from ctrlora_b200.train import FinetuneTrainer
+        torch.manual_seed(0)  # replicas start from identical weights
+        model = create_model(os.path.join(ROOT, "tests", "golden", "tiny_finetune.yaml"))
+        trainer = FinetuneTrainer(model)
+        assert trainer.world == world
+        G = trainer.G
+        # parameters alias the flat buffer
+        p0 = G.params[0]
+        G.flat_p[0] = 123.0
+        assert p0.reshape(-1)[0].item() == 123.0
+        # rank-dependent gradients -> one all-reduce -> identical sums on every rank
+        gen = torch.Generator().manual_seed(100 + rank)
+        G.flat_g.copy_(torch.randn(G.numel, generator=gen))
+        mine = G.flat_g.clone()
+        trainer.reduce_gradients()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        expect = sum(gathered)
+        ok = torch.allclose(G.flat_g, expect, atol=1e-6)
+        sums = [torch.empty(1) for _ in range(world)]
+        dist.all_gather(sums, G.flat_g.sum().reshape(1))
+        same = all(torch.equal(sums[0], s) for s in sums)
+        q.put((rank, ok, same, G.numel, len(G.names)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, same, numel, n in res:
+        assert ok and same, (rank, ok, same)
+        assert n == 246  # LoRA 164 + zero-convs 26 + norms 56 tensors, like the reference's optimizer
+    assert res[0][3] == res[1][3]

@@ -48,7 +48,11 @@ def test_loss_and_gradients_vs_reference_autograd(setup):
     print(f"train eps rel err {e_eps:.2e}, loss rel err {e_loss:.2e}")
     assert e_eps < 3e-3 and e_loss < 3e-3
     grads = trainer.G.named_grads()
-    floor = 1e-4 * max(g["grad_norms"].values())  # level-1 emb_layers grads are exactly cancelled (see oracle test)
+    # four tensors (input_blocks.{1,2}.0.emb_layers.1 LoRA) have mathematically zero gradients in this config (32
+    # channels / 32 groups: the GroupNorm cancels the time-embedding offset; reference norms ~1e-9): they are checked
+    # against an absolute floor of 1 % of the median gradient norm instead of relatively
+    norms = sorted(g["grad_norms"].values())
+    floor = 1e-2 * norms[len(norms) // 2]
     worst = 0.0
     for n, ref in g["grad_norms"].items():
         got = grads[n].norm().item()
