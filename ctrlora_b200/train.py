@@ -560,8 +560,37 @@ class FinetuneTrainer:
         if self.world > 1:
             torch.distributed.all_reduce(self.G.flat_g, group=self.pg)
 
+    # -- CUDA-graph replay of forward + backward (≈3 000 launches per step; Python cannot enqueue them fast enough)
+    def capture(self, x0, hint_latent, context, t, noise, warmup=2):
+        """Capture loss_and_grads for these shapes.  The LoRA folds / transposes of the trainable parameters are part
+        of the graph (they must re-run every step), the frozen-weight copies are built during warm-up and are not."""
+        self._static = [v.clone() for v in (x0, hint_latent, context, t, noise)]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.loss_and_grads(*self._static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        prepare.bump_train_version()  # force the trainable-weight preparation into the captured region
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.loss_and_grads(*self._static)
+        return self
+
+    def loss_and_grads_graphed(self, x0, hint_latent, context, t, noise):
+        for dst, src in zip(self._static, (x0, hint_latent, context, t, noise)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
     def step(self, x0, hint_latent, context, t, noise):
-        loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
+        if getattr(self, "_graph", None) is not None:
+            loss = self.loss_and_grads_graphed(x0, hint_latent, context, t, noise)
+        else:
+            loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
         self.reduce_gradients()
         self.step_count += 1
         ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,

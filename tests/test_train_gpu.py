@@ -49,16 +49,20 @@ def test_loss_and_gradients_vs_reference_autograd(setup):
     assert e_eps < 3e-3 and e_loss < 3e-3
     grads = trainer.G.named_grads()
     # four tensors (input_blocks.{1,2}.0.emb_layers.1 LoRA) have mathematically zero gradients in this config (32
-    # channels / 32 groups: the GroupNorm cancels the time-embedding offset; reference norms ~1e-9): they are checked
-    # against an absolute floor of 1 % of the median gradient norm instead of relatively
+    # channels / 32 groups: the GroupNorm cancels the time-embedding offset; reference norms ~1e-9)
     norms = sorted(g["grad_norms"].values())
-    floor = 1e-2 * norms[len(norms) // 2]
-    worst = 0.0
+    median, biggest = norms[len(norms) // 2], norms[-1]
+    worst, n_zero = 0.0, 0
     for n, ref in g["grad_norms"].items():
         got = grads[n].norm().item()
-        err = abs(got - ref) / (ref + floor)
+        if ref < 1e-5 * biggest:  # mathematically zero: ours must be noise (< 1 % of the median gradient norm)
+            assert got < 1e-2 * median, (n, got, ref)
+            n_zero += 1
+            continue
+        err = abs(got - ref) / ref
         worst = max(worst, err)
         assert err < 3e-2, (n, got, ref)
+    assert n_zero == 4
     errs = {n: rel(grads[n], ref) for n, ref in g["grads"].items()}
     print("grad norm worst rel err %.2e; full-tensor rel errs:" % worst, {k[-40:]: "%.1e" % v for k, v in errs.items()})
     # fp16 activations/gradients through ~60 layers: 2e-2 norm-relative on individual tensors
