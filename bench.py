@@ -189,6 +189,75 @@ def workload_config(n):
             "l2": "no flush needed: 2.7 GB of fp16 weights stream through the 126 MB L2 every step"}
 
 
+TRAIN_BATCH = 16
+TF_PER_IMAGE_TRAIN = 2.11  # algorithmically necessary TFLOP per image of one finetune step at rank 128
+
+
+def run_train(args, rank, local_rank, world, device):
+    """BASELINE.json configs[2]: ctrlora_finetune_sd15_rank128 training step, synthetic pairs, batch 16 per GPU,
+    data-parallel with ONE NCCL all-reduce of the flat trainable-gradient buffer per step.  Returns a dict."""
+    import torch.distributed as dist
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from ctrlora_b200.train import FinetuneTrainer
+    model = build_model(device, seed=0)  # identical replicas
+    trainer = FinetuneTrainer(model, lr=1e-5)
+    B = TRAIN_BATCH
+    gen = torch.Generator().manual_seed(200 + rank)
+    host = {"x0": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "hint": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "ctx": torch.randn(B, CTX_TOKENS, CTX_DIM, generator=gen).pin_memory(),
+            "t": torch.randint(0, 1000, (B,), generator=gen).pin_memory(),
+            "noise": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory()}
+    order = ("x0", "hint", "ctx", "t", "noise")
+    dev = [host[k].to(device) for k in order]
+    trainer.capture(*dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        trainer.step(*dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(*dev)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    loss_host = torch.empty(1).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in order)
+    for _ in range(2):
+        trainer.step(*[host[k].to(device, non_blocking=True) for k in order])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(*[host[k].to(device, non_blocking=True) for k in order])
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    peak_tf, _, peak_src = measured_peaks()
+    ips = world * B * args.steps / (ms_dev / 1e3)
+    return {"metric": "train_images_per_sec", "value": ips, "unit": "images/s (512x512, rank 128)", "batch_per_gpu": B,
+            "ms_per_step": ms_dev / args.steps, "loss": float(loss_host.item()),
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "allreduce_bytes_per_step": trainer.G.numel * 4 if world > 1 else 0, "trainable_params": trainer.G.numel,
+            "roofline": {"bound": "tensor", "achieved": ips / world * TF_PER_IMAGE_TRAIN, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ips / world * TF_PER_IMAGE_TRAIN / peak_tf, "peak_source": peak_src,
+                         "note": "algorithmically necessary 2.11 TFLOP/image (no recompute, no frozen weight grads)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +265,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sample+train", choices=["sample", "train", "sample+train"],
+                    help="sample: configs[1] DDIM step (the headline line); train: configs[2] finetune step; default: both, "
+                         "the training result rides in the line's 'train' key")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     args.warmup = max(args.warmup, 3)
@@ -210,6 +282,20 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from ctrlora_b200 import dropin, ops
     dropin.activate()
+    if args.workload == "train":
+        res = run_train(args, rank, local_rank, world, device)
+        if rank == 0:
+            line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "fp16 (fp32 accumulate, fp32 master weights)", "data": "synthetic",
+                    "config": {"workload": "configs[2]: ctrlora_finetune_sd15_rank128 training step, synthetic pairs, batch 16 "
+                                           "per GPU, 512x512 (latent 4x64x64)", "batch_per_gpu": TRAIN_BATCH,
+                               "parallelism": f"dp{world}"},
+                    "e2e": res["e2e"], "roofline": res["roofline"], "train": res}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     from cldm.ddim_hacked import DDIMSampler
     model = build_model(device, seed=rank)
     sampler = DDIMSampler(model, batched_cfg=True, use_cuda_graph=True)
@@ -292,6 +378,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = t.tolist()
+    train_result = None
+    if "train" in args.workload:
+        del sampler, model
+        torch.cuda.empty_cache()
+        train_result = run_train(args, rank, local_rank, world, device)
     if rank == 0:
         peak_tf, peak_hbm, peak_src = measured_peaks()
         value = world * args.steps / (ms_dev / 1e3)
@@ -311,6 +402,8 @@ def main():
                              "peak_source": peak_src + ", sustained bf16/fp16 dense", "traffic": None,
                              "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,
                              "share_of_step": gemm_stats["ms"] / (ms_dev / args.steps)}}
+        if train_result is not None:
+            line["train"] = train_result
         if not args.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)  # torch's intra-op scaling on this model collapses beyond ~32 threads
             sd = cpu_state_dict()
