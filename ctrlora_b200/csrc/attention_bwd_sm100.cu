@@ -94,7 +94,7 @@ struct DqSmem {
 };
 
 template <int DPAD, int BKV>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS, (2 * BKV + DPAD <= 256) ? 2 : 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ AttnBwdParams p) {
@@ -106,6 +106,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA);
     uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *ds_full = bars + 4, *acc_done = bars + 5;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    constexpr uint32_t TMEM_COLS = (2 * BKV + DPAD <= 256) ? 256 : 512;  // 256 columns: two CTAs share an SM's TMEM
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
     if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
@@ -114,7 +115,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(ds_full, 128); mbar_init(acc_done, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    if (warp == 0) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -233,7 +234,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ================================================================================================ dK, dV
@@ -251,7 +252,7 @@ struct DkvSmem {
 };
 
 template <int DPAD, int BQ>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS, (2 * BQ + 2 * DPAD <= 256) ? 2 : 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ AttnBwdParams p) {
@@ -266,6 +267,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
     uint64_t *kv_full = bars, *q_full = bars + 1, *q_free = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *acc_done = bars + 5;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    constexpr uint32_t TMEM_COLS = (2 * BQ + 2 * DPAD <= 256) ? 256 : 512;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
     if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
@@ -274,7 +276,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_init(p_full, 128); mbar_init(acc_done, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    if (warp == 0) tmem_alloc(tmem_ptr, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -407,7 +409,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 template <int DPAD, int BKV>
@@ -477,7 +479,7 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
     const bool wide = d > 80;
     // ---- dQ: 128-query CTAs, key tiles of 128 (64 for d_head 160)
     {
-        const int bkv = wide ? 64 : 128;
+        const int bkv = (wide || d <= 48) ? 64 : 128;  // d <= 48: 64-key tiles keep TMEM at 256 columns -> 2 CTAs per SM
         CUtensorMap tq, tdo, tk, tv;
         int rc = tmap_tokens(&tq, q, ldq, d, heads, nq, batch, 128);
         if (!rc) rc = tmap_tokens(&tdo, dout, lddo, d, heads, nq, batch, 128);
@@ -486,14 +488,14 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
         if (rc) return rc;
         p.idesc_s = umma_idesc_f16(128, bkv, 0);
         dim3 grid((nq + 127) / 128, heads, batch);
-        if (d <= 48) rc = launch_dq<48, 128>(tq, tdo, tk, tv, p, grid, stream);
+        if (d <= 48) rc = launch_dq<48, 64>(tq, tdo, tk, tv, p, grid, stream);
         else if (d <= 80) rc = launch_dq<80, 128>(tq, tdo, tk, tv, p, grid, stream);
         else rc = launch_dq<160, 64>(tq, tdo, tk, tv, p, grid, stream);
         if (rc) return rc;
     }
     // ---- dK, dV: 128-key CTAs, query tiles of 128 (64 for d_head 160)
     {
-        const int bq = wide ? 64 : 128;
+        const int bq = (wide || d <= 48) ? 64 : 128;
         CUtensorMap tq, tdo, tk, tv;
         int rc = tmap_tokens(&tq, q, ldq, d, heads, nq, batch, bq);
         if (!rc) rc = tmap_tokens(&tdo, dout, lddo, d, heads, nq, batch, bq);
@@ -502,7 +504,7 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
         if (rc) return rc;
         p.idesc_s = umma_idesc_f16(128, bq, 0);
         dim3 grid((nk + 127) / 128, heads, batch);
-        if (d <= 48) rc = launch_dkdv<48, 128>(tq, tdo, tk, tv, p, grid, stream);
+        if (d <= 48) rc = launch_dkdv<48, 64>(tq, tdo, tk, tv, p, grid, stream);
         else if (d <= 80) rc = launch_dkdv<80, 128>(tq, tdo, tk, tv, p, grid, stream);
         else rc = launch_dkdv<160, 64>(tq, tdo, tk, tv, p, grid, stream);
         if (rc) return rc;
