@@ -226,6 +226,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
+        } else if (p.residual && p.splits == 1) {
+            // ------------------------------------------------ lanes 1-31: pull the residual rows of this CTA's tiles into L2
+            // well ahead of the epilogue (its per-row residual reads are otherwise a full DRAM latency each)
+            const int esz = p.residual_f32 ? 4 : 2;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int mt, ks, nt;
+                decode(tile, mt, ks, nt);
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+                const int n0 = nt * bn_out;
+                const int nbytes = min(bn_out, p.N - n0) * esz;
+                for (int r = lane - 1; r < GEMM_BM; r += 31) {
+                    const int gw = tw * p.bw + r % p.bw, gh = th * p.bh + (r / p.bw) % p.bh, gb = tb * p.nb + r / (p.bw * p.bh);
+                    if (gw < p.W && gh < p.H && gb < p.Bn) {
+                        const long long m = (static_cast<long long>(gb) * p.H + gh) * p.W + gw;
+                        const char* row = reinterpret_cast<const char*>(p.residual) + (m * p.ldr + n0) * esz;
+                        for (int off = 0; off < nbytes; off += 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off) : "memory");
+                    }
+                }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
