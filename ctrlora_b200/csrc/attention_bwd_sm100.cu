@@ -189,18 +189,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tmem_ld_32x32(tm_s + lane_off + c, sr);
                 tmem_ld_32x32(tm_dp + lane_off + c, dr);
                 tmem_ld_wait();
+                if (kv_valid == BKV) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float ds0 = 0.f, ds1 = 0.f;
-                    if (c + i < kv_valid) {
-                        const float pr = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse));
-                        ds0 = pr * (__uint_as_float(dr[i]) - dl);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse));
+                        packed[i >> 1] = pack_half2(p0 * (__uint_as_float(dr[i]) - dl), p1 * (__uint_as_float(dr[i + 1]) - dl));
                     }
-                    if (c + i + 1 < kv_valid) {
-                        const float pr = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse));
-                        ds1 = pr * (__uint_as_float(dr[i + 1]) - dl);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float ds0 = 0.f, ds1 = 0.f;
+                        if (c + i < kv_valid) {
+                            const float pr = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse));
+                            ds0 = pr * (__uint_as_float(dr[i]) - dl);
+                        }
+                        if (c + i + 1 < kv_valid) {
+                            const float pr = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse));
+                            ds1 = pr * (__uint_as_float(dr[i + 1]) - dl);
+                        }
+                        packed[i >> 1] = pack_half2(ds0, ds1);
                     }
-                    packed[i >> 1] = pack_half2(ds0, ds1);
                 }
                 store_row_chunk(sDS, 128, r, c, packed);
             }
@@ -356,19 +365,37 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld_32x32(tm_s + lane_off + c, sr);
                 tmem_ld_32x32(tm_dp + lane_off + c, dr);
                 tmem_ld_wait();
+                float ls[32], de[32];
 #pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                    if (key_ok && c + t < q_valid) {
-                        p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -sLse[c + t]));
-                        d0 = p0 * (__uint_as_float(dr[t]) - sDel[c + t]);
+                for (int t = 0; t < 32; t += 4) {  // broadcast 16-byte shared loads: every lane reads the same columns
+                    const float4 a4 = *reinterpret_cast<const float4*>(sLse + c + t);
+                    const float4 b4 = *reinterpret_cast<const float4*>(sDel + c + t);
+                    ls[t] = a4.x; ls[t + 1] = a4.y; ls[t + 2] = a4.z; ls[t + 3] = a4.w;
+                    de[t] = b4.x; de[t + 1] = b4.y; de[t + 2] = b4.z; de[t + 3] = b4.w;
+                }
+                if (key_ok && q_valid == BQ) {
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -ls[t]));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -ls[t + 1]));
+                        pp[t >> 1] = pack_half2(p0, p1);
+                        dd[t >> 1] = pack_half2(p0 * (__uint_as_float(dr[t]) - de[t]), p1 * (__uint_as_float(dr[t + 1]) - de[t + 1]));
                     }
-                    if (key_ok && c + t + 1 < q_valid) {
-                        p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -sLse[c + t + 1]));
-                        d1 = p1 * (__uint_as_float(dr[t + 1]) - sDel[c + t + 1]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                        if (key_ok && c + t < q_valid) {
+                            p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -ls[t]));
+                            d0 = p0 * (__uint_as_float(dr[t]) - de[t]);
+                        }
+                        if (key_ok && c + t + 1 < q_valid) {
+                            p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -ls[t + 1]));
+                            d1 = p1 * (__uint_as_float(dr[t + 1]) - de[t + 1]);
+                        }
+                        pp[t >> 1] = pack_half2(p0, p1);
+                        dd[t >> 1] = pack_half2(d0, d1);
                     }
-                    pp[t >> 1] = pack_half2(p0, p1);
-                    dd[t >> 1] = pack_half2(d0, d1);
                 }
                 store_row_chunk(sPT, 128, r, c, pp);
                 store_row_chunk(sDST, 128, r, c, dd);

@@ -21,29 +21,24 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // then the store (row-major fp16 / fp32, or the transposed V^T layout).  v = value columns, g = gate columns (GEGLU).
 template <bool GEGLU>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, const float* g, int c, int bn_out, int n0,
-                                               bool row_ok, long long m, int img, int tok, const uint4* rpre = nullptr) {
+                                               bool row_ok, long long m, int img, int tok, const float* sb,
+                                               const uint4* rpre = nullptr) {
     const int nbase = n0 + c;
     const bool full_chunk = (c + 32 <= bn_out) && (nbase + 32 <= p.N);
-    if (p.bias) {
-        if (full_chunk) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + nbase);
+    // sb: this tile's bias staged in shared memory (zeros where there is no bias / beyond N): broadcast 16-byte reads
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 b4 = __ldg(bp + q);
-                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (nbase + j < p.N) v[j] += __ldg(p.bias + nbase + j);
-        }
+    for (int q = 0; q < 8; ++q) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+        v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
     }
     if (GEGLU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float gg = g[j];
-            if (p.bias && nbase + j < p.N) gg += __ldg(p.bias + p.N + nbase + j);
-            v[j] *= gelu_erf_f(gg);
+        for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * q);
+            v[4 * q] *= gelu_erf_f(g[4 * q] + b4.x);
+            v[4 * q + 1] *= gelu_erf_f(g[4 * q + 1] + b4.y);
+            v[4 * q + 2] *= gelu_erf_f(g[4 * q + 2] + b4.z);
+            v[4 * q + 3] *= gelu_erf_f(g[4 * q + 3] + b4.w);
         }
     }
     if (!row_ok) return;
@@ -148,6 +143,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tempty = bars + 2 * GEMM_MAX_STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4);
     volatile int* last_flag = reinterpret_cast<volatile int*>(bars + 2 * GEMM_MAX_STAGES + 5);
+    float* sbias_all = reinterpret_cast<float*>(smem + GEMM_SMEM_DATA + 512);  // [2 tile parities][value 256 | gate 256]
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -226,26 +222,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
-        } else if (p.residual && p.splits == 1) {
-            // ------------------------------------------------ lanes 1-31: pull the residual rows of this CTA's tiles into L2
-            // well ahead of the epilogue (its per-row residual reads are otherwise a full DRAM latency each)
-            const int esz = p.residual_f32 ? 4 : 2;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int mt, ks, nt;
-                decode(tile, mt, ks, nt);
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int n0 = nt * bn_out;
-                const int nbytes = min(bn_out, p.N - n0) * esz;
-                for (int r = lane - 1; r < GEMM_BM; r += 31) {
-                    const int gw = tw * p.bw + r % p.bw, gh = th * p.bh + (r / p.bw) % p.bh, gb = tb * p.nb + r / (p.bw * p.bh);
-                    if (gw < p.W && gh < p.H && gb < p.Bn) {
-                        const long long m = (static_cast<long long>(gb) * p.H + gh) * p.W + gw;
-                        const char* row = reinterpret_cast<const char*>(p.residual) + (m * p.ldr + n0) * esz;
-                        for (int off = 0; off < nbytes; off += 128)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off) : "memory");
-                    }
-                }
-            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -287,7 +263,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int iw = r % p.bw, ih = (r / p.bw) % p.bh, ib = r / (p.bw * p.bh);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        uint4 rres[3][4];
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
             int mt, ks, nt;
             decode(tile, mt, ks, nt);
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
@@ -298,20 +276,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int img = row_ok ? static_cast<int>(m / p.rows_per_img) : 0;
             const int tok = row_ok ? static_cast<int>(m % p.rows_per_img) : 0;
 
-            // issue this tile's residual loads now: they complete while the tile's MMAs are still running
-            uint4 rres[3][4];
-            const bool res16 = !GEGLU && p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && row_ok && p.splits == 1;
-            if (res16) {
+            // ---- stage this tile's bias in shared memory (double-buffered by tile parity)
+            float* sb = sbias_all + (tile_iter & 1) * 512;
+            {
+                const int e = threadIdx.x - 64;  // 0..255 over the epilogue warps
+                float bv = 0.f, bg = 0.f;
+                if (p.bias && e < bn_out && n0 + e < p.N) {
+                    bv = __ldg(p.bias + n0 + e);
+                    if (GEGLU) bg = __ldg(p.bias + p.N + n0 + e);
+                }
+                sb[e] = bv;
+                if (GEGLU) sb[256 + e] = bg;
+            }
+            // ---- residual: registers hold THIS tile's chunks (loaded while the previous tile was being finished)
+            const bool res16 = !GEGLU && p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && p.splits == 1;
+            auto load_res = [&](uint4* dst, long long mm, int nn0, int c) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + mm * p.ldr + nn0 + c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = __ldg(rp + q);
+            };
+            if (res16 && tile_iter == 0 && row_ok) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int c = 32 * half + 64 * i;
-                    if (c + 32 <= bn_out && n0 + c + 32 <= p.N) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + c);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) rres[i][q] = __ldg(rp + q);
-                    }
+                    if (c + 32 <= bn_out && n0 + c + 32 <= p.N) load_res(rres[i], m, n0, c);
                 }
             }
+            // coordinates of this CTA's next tile (for the refill of the residual registers)
+            bool nrow_ok = false;
+            long long nm = 0;
+            int nn0 = 0;
+            if (res16 && tile + static_cast<int>(gridDim.x) < total_tiles) {
+                int mt2, ks2, nt2;
+                decode(tile + gridDim.x, mt2, ks2, nt2);
+                const int tw2 = mt2 % p.tiles_w, th2 = (mt2 / p.tiles_w) % p.tiles_h, tb2 = mt2 / (p.tiles_w * p.tiles_h);
+                const int gw2 = tw2 * p.bw + iw, gh2 = th2 * p.bh + ih, gb2 = tb2 * p.nb + ib;
+                nrow_ok = gw2 < p.W && gh2 < p.H && gb2 < p.Bn;
+                nm = (static_cast<long long>(gb2) * p.H + gh2) * p.W + gw2;
+                nn0 = nt2 * bn_out;
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");  // bias staged
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
@@ -335,8 +339,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    const bool pre = res16 && i < 3 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
-                    epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, pre ? rres[i < 3 ? i : 0] : nullptr);
+                    const bool pre = res16 && row_ok && i < 3 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
+                    epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, sb, pre ? rres[i < 3 ? i : 0] : nullptr);
+                    // refill the slot with the same chunk of this CTA's NEXT tile: a whole tile of lead time
+                    if (res16 && nrow_ok && i < 3 && (c + 32 <= bn_out) && (nn0 + c + 32 <= p.N)) load_res(rres[i < 3 ? i : 0], nm, nn0, c);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -391,7 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
                             g[4 * q] = g4.x; g[4 * q + 1] = g4.y; g[4 * q + 2] = g4.z; g[4 * q + 3] = g4.w;
                         }
-                        epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok);
+                        epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, sb);
                     }
                 }
                 // nobody may overwrite last_flag before every epilogue thread has read it

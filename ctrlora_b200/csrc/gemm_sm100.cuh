@@ -11,7 +11,7 @@ constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KiB
 constexpr int GEMM_EPI_WARPS = 8;       // two warps per TMEM lane group, interleaved over 32-column chunks
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer, then epilogue
 constexpr int GEMM_SMEM_DATA = 216 * 1024;            // ring buffer budget
-constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_DATA + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_DATA + 1024 /*align slack*/ + 512 /*barriers*/ + 4096 /*bias staging*/;
 
 struct GemmKParams {
     // tile geometry over the (B, H, W) pixel grid; a plain [M, K] matrix is B=1, H=1, W=M
