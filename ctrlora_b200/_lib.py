@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
         ("head_dim", c_int), ("tok_pad", c_int), ("bf16", c_int),
         ("split_k", c_int), ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_ll),
         ("splitk_counters", c_void_p), ("splitk_counters_len", c_int),
-        ("dup_out", c_void_p), ("dup_ld", c_int),
+        ("dup_out", c_void_p), ("dup_ld", c_int), ("force_single_cta", c_int),
     ]
 
 

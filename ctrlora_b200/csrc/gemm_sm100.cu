@@ -129,7 +129,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool GEGLU>
+template <bool GEGLU, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -149,6 +149,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nstages = p.stages;
+    // PAIR: two CTAs (a cluster) own one 256-row tile: tcgen05.mma.cta_group::2 issued by CTA 0 reads A (128 rows) and
+    // half of B (BN/2 rows) from EACH CTA's shared memory, so every SM ingests half the B bytes per flop.
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -165,27 +169,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], GEMM_EPI_WARPS);
+            mbar_init(&tempty[i], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, 512);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_2cta(tmem_ptr, 512);
+        else tmem_alloc(tmem_ptr, 512);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / TMA completion targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();  // everything above overlapped the previous kernel's tail; operands are read only from here on
 
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-    const int total_tiles = m_tiles * p.n_tiles * p.splits;
+    const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;  // scheduling units along M (pairs of 128-row tiles)
+    const int total_tiles = m_units * p.n_tiles * p.splits;
+    const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int main_iters = p.taps * p.kchunks;
     const int k_iters = main_iters + p.kchunks2;
     const int bn_out = GEGLU ? (p.BN >> 1) : p.BN;
 
     // tile -> (m tile, split, n tile); the k range of a split is [ks * kiters_per_split, ...)
     auto decode = [&](int tile, int& mt, int& ks, int& nt) {
-        mt = tile % m_tiles;
-        const int rest = tile / m_tiles;
+        mt = tile % m_units;
+        if (PAIR) mt = 2 * mt + static_cast<int>(rank);  // an odd tile count leaves a phantom tile: all-OOB loads, masked rows
+        const int rest = tile / m_units;
         ks = rest % p.splits;
         nt = rest / p.splits;
     };
@@ -195,8 +207,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ------------------------------------------------ TMA producer
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = GEMM_A_BYTES + p.BN * 128;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const uint32_t tx_bytes = PAIR ? 2 * (GEMM_A_BYTES + (p.BN >> 1) * 128) : GEMM_A_BYTES + p.BN * 128;
+            for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
                 int mt, ks, nt;
                 decode(tile, mt, ks, nt);
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
@@ -206,8 +218,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* a_dst = smem + stage * p.stage_bytes;
                     uint8_t* b_dst = a_dst + GEMM_A_BYTES;
-                    mbar_expect_tx(&full[stage], tx_bytes);
-                    if (it < main_iters) {
+                    if (!PAIR || leader) mbar_expect_tx(&full[stage], tx_bytes);  // PAIR: both CTAs' bytes land on CTA 0's barrier
+                    if (PAIR) {
+                        // this CTA's half of the B rows: GEGLU -> CTA 0 value rows, CTA 1 gate rows; else the two N halves
+                        const int brow = GEGLU ? (leader ? n0 : p.N + n0) : n0 + static_cast<int>(rank) * (p.BN >> 1);
+                        if (it < main_iters) {
+                            const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                            const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
+                            tma_load_4d_2cta(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
+                            tma_load_3d_2cta(b_dst, &tmB, &full[stage], kc * GEMM_BK, tap, brow);
+                        } else {
+                            const int kc = it - main_iters;
+                            tma_load_4d_2cta(a_dst, &tmA2, &full[stage], kc * GEMM_BK, w0, h0, b0);
+                            tma_load_3d_2cta(b_dst, &tmB2, &full[stage], kc * GEMM_BK, 0, brow);
+                        }
+                    } else if (it < main_iters) {
                         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
                         const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
                         tma_load_4d(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
@@ -224,13 +249,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0 && leader) {
+            // ------------------------------------------------ MMA issuer (single thread; CTA 0 issues for the pair)
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
                 int mt, ks, nt;
                 decode(tile, mt, ks, nt);
                 const int it0 = ks * p.kiters_per_split, it1 = min(k_iters, it0 + p.kiters_per_split);
@@ -244,13 +269,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t b_addr = a_addr + GEMM_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        umma_f16(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                                 p.idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        if (PAIR)
+                            umma_f16_2cta(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
+                                          p.idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        else
+                            umma_f16(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
+                                     p.idesc, (it > it0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+                    if (PAIR) umma_commit_2cta(&empty[stage]); else umma_commit(&empty[stage]);
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (PAIR) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -265,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t acc_phase = 0;
         uint4 rres[3][4];
         int tile_iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
+        for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++tile_iter) {
             int mt, ks, nt;
             decode(tile, mt, ks, nt);
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
@@ -306,9 +336,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bool nrow_ok = false;
             long long nm = 0;
             int nn0 = 0;
-            if (res16 && tile + static_cast<int>(gridDim.x) < total_tiles) {
+            if (res16 && tile + tile_stride < total_tiles) {
                 int mt2, ks2, nt2;
-                decode(tile + gridDim.x, mt2, ks2, nt2);
+                decode(tile + tile_stride, mt2, ks2, nt2);
                 const int tw2 = mt2 % p.tiles_w, th2 = (mt2 / p.tiles_w) % p.tiles_h, tb2 = mt2 / (p.tiles_w * p.tiles_h);
                 const int gw2 = tw2 * p.bw + iw, gh2 = th2 * p.bh + ih, gb2 = tb2 * p.nb + ib;
                 nrow_ok = gw2 < p.W && gh2 < p.H && gb2 < p.Bn;
@@ -346,7 +376,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]); }
             } else {
                 // ---- split-K: park this split's partial tile in its own fp32 workspace slice (plain stores)
                 const int tile_mn = nt * m_tiles + mt;
@@ -409,9 +439,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer may still be reading this CTA's shared memory / signalling its barriers
     if (warp == 2) {
         __syncwarp();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_2cta(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -551,10 +583,18 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         p.ws = a->splitk_ws;
         p.counters = a->splitk_counters;
     }
-    p.stage_bytes = GEMM_A_BYTES + ((p.BN * 128 + 1023) / 1024) * 1024;
+    // ---- 2-CTA pairs (cta_group::2): every SM ingests half of the B tile; needs an even split of N and no split-K
+    static int pair_env = -1;
+    if (pair_env < 0) {
+        const char* e = getenv("CTRLORA_GEMM_PAIR");
+        pair_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool pair = pair_env && p.splits == 1 && (p.BN % 32 == 0) && g_num_sms >= 2 && a->force_single_cta == 0;
+    const int b_rows = pair ? p.BN / 2 : p.BN;  // B rows held by one CTA
+    p.stage_bytes = GEMM_A_BYTES + ((b_rows * 128 + 1023) / 1024) * 1024;
     p.stages = GEMM_SMEM_DATA / p.stage_bytes;
     if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
-    p.idesc = umma_idesc_f16(GEMM_BM, p.BN, 0);
+    p.idesc = umma_idesc_f16(pair ? 2 * GEMM_BM : GEMM_BM, p.BN, 0);
     for (int i = 0; i < 3; ++i) { p.out[i] = a->out[i]; p.transposed[i] = a->transposed[i]; }
     p.seg_width = a->seg_width;
     p.ldc = a->ldc; p.out_f32 = a->out_f32;
@@ -577,7 +617,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         const uint64_t rows = p.geglu ? 2ull * p.N : (uint64_t)p.N;
         uint64_t wd[3] = {(uint64_t)a->a_c, (uint64_t)p.taps, rows};
         uint64_t ws[2] = {(uint64_t)a->a_c * 2, (uint64_t)a->a_c * 2 * p.taps};
-        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)bn_out};
+        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)((pair && !p.geglu) ? p.BN / 2 : bn_out)};
         rc = make_tmap_f16(&tmB, a->w, 3, wd, ws, wb);
         if (rc) return rc;
     }
@@ -590,7 +630,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         if (rc) return rc;
         uint64_t wd[3] = {(uint64_t)a->a2_c, 1, (uint64_t)p.N};
         uint64_t ws[2] = {(uint64_t)a->a2_c * 2, (uint64_t)a->a2_c * 2};
-        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)bn_out};
+        uint32_t wb[3] = {GEMM_BK, 1, (uint32_t)(pair ? p.BN / 2 : bn_out)};
         rc = make_tmap_f16(&tmB2, a->w2, 3, wd, ws, wb);
         if (rc) return rc;
     } else {
@@ -598,17 +638,29 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         tmB2 = tmB;
     }
     if (!g_attr_set) {
-        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess)
             return CTRLORA_ERR_CUDA;
         g_attr_set = true;
     }
-    const int total = m_tiles * p.n_tiles * p.splits;
-    const int grid = total < g_num_sms ? total : g_num_sms;
-    const cudaError_t lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                                 stream, tmA, tmB, tmA2, tmB2, p)
-                                    : launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                                 stream, tmA, tmB, tmA2, tmB2, p);
+    cudaError_t lrc;
+    if (pair) {
+        const int units = ((m_tiles + 1) / 2) * p.n_tiles;           // one unit = one 256-row tile for one CTA pair
+        int clusters = g_num_sms / 2;
+        if (units < clusters) clusters = units;
+        const dim3 grid2(2 * clusters), block(GEMM_THREADS);
+        lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, p)
+                      : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, p);
+    } else {
+        const int total = m_tiles * p.n_tiles * p.splits;
+        const int grid = total < g_num_sms ? total : g_num_sms;
+        lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
+                                   stream, tmA, tmB, tmA2, tmB2, p)
+                      : launch_pdl(gemm_tcgen05_kernel<false, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
+                                   stream, tmA, tmB, tmA2, tmB2, p);
+    }
     if (lrc != cudaSuccess) return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }

@@ -94,7 +94,7 @@ def _as_bhwc(a):
 def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0, residual=None, out_scale=1.0, a2=None,
          w2=None,
          geglu=False, out=None, out_f32=False, seg_outs=None, seg_width=0, transposed=(0, 0, 0), head_dim=0,
-         tok_pad=0, block_n=0, split_k=0, dup_out=None, simt=False):
+         tok_pad=0, block_n=0, split_k=0, dup_out=None, single_cta=False, simt=False):
     """out = epilogue(conv_or_linear(a, w) [+ a2 @ w2^T]); see `ctrlora_gemm_f16` in include/ctrlora_b200.h.
 
     a: fp16 [B,H,W,C] or [M,K]; w: fp16 [N(2N), ksize*ksize, C]; returns the output tensor ([..., N]).
@@ -146,6 +146,7 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
     args.splitk_counters, args.splitk_counters_len = cnt.data_ptr(), SPLITK_COUNTERS
     if dup_out is not None:
         args.dup_out, args.dup_ld = dup_out.data_ptr(), dup_out.stride(0)
+    args.force_single_cta = int(single_cta)
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
     _count()

@@ -75,6 +75,7 @@ typedef struct ctrlora_gemm_args {
     int splitk_counters_len;
     void* dup_out;          /* optional: transposed segments are also stored row-major here (fp16, row stride dup_ld) */
     int dup_ld;
+    int force_single_cta;   /* 1: never use the 2-CTA (cta_group::2) tile pairs (tests / bisecting) */
 } ctrlora_gemm_args;
 
 int ctrlora_gemm_f16(const ctrlora_gemm_args* args, void* stream);
