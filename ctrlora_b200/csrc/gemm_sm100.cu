@@ -146,7 +146,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* sbias_all = reinterpret_cast<float*>(smem + GEMM_SMEM_DATA + 512);  // [2 tile parities][value 256 | gate 256]
 
     pdl_launch_dependents();
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const int nstages = p.stages;
     // PAIR: two CTAs (a cluster) own one 256-row tile: tcgen05.mma.cta_group::2 issued by CTA 0 reads A (128 rows) and
@@ -203,84 +203,107 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            int stage = 0;
-            uint32_t phase = 0;
+        {
+            // ------------------------------------------------ TMA producer (whole warp loops; one elected lane issues)
+            // One thread; its loop body is the serial critical path of the whole pipeline (measured: the first version
+            // spent ~650 cycles per k-step in integer div/mod and address math, which capped every conv at ~40 % of the
+            // tensor pipe regardless of tile width). Everything is strength-reduced to counters and raw shared addresses.
             const uint32_t tx_bytes = PAIR ? 2 * (GEMM_A_BYTES + (p.BN >> 1) * 128) : GEMM_A_BYTES + p.BN * 128;
+            const int kchunks = p.kchunks, kw = p.kw, pad = p.pad, kps = p.kiters_per_split;
+            const uint32_t stage_bytes = static_cast<uint32_t>(p.stage_bytes);
+            const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
+            const uint32_t gate_off = GEMM_A_BYTES + static_cast<uint32_t>(bn_out) * 128;
+            int stage = 0;
+            uint32_t phase = 0, a_dst = smem0, fb = full0, eb = empty0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
                 int mt, ks, nt;
                 decode(tile, mt, ks, nt);
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.bw, h0 = th * p.bh, b0 = tb * p.nb, n0 = nt * bn_out;
-                const int it0 = ks * p.kiters_per_split, it1 = min(k_iters, it0 + p.kiters_per_split);
-                for (int it = it0; it < it1; ++it) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* a_dst = smem + stage * p.stage_bytes;
-                    uint8_t* b_dst = a_dst + GEMM_A_BYTES;
-                    if (!PAIR || leader) mbar_expect_tx(&full[stage], tx_bytes);  // PAIR: both CTAs' bytes land on CTA 0's barrier
-                    if (PAIR) {
-                        // this CTA's half of the B rows: GEGLU -> CTA 0 value rows, CTA 1 gate rows; else the two N halves
-                        const int brow = GEGLU ? (leader ? n0 : p.N + n0) : n0 + static_cast<int>(rank) * (p.BN >> 1);
-                        if (it < main_iters) {
-                            const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                            const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
-                            tma_load_4d_2cta(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
-                            tma_load_3d_2cta(b_dst, &tmB, &full[stage], kc * GEMM_BK, tap, brow);
-                        } else {
-                            const int kc = it - main_iters;
-                            tma_load_4d_2cta(a_dst, &tmA2, &full[stage], kc * GEMM_BK, w0, h0, b0);
-                            tma_load_3d_2cta(b_dst, &tmB2, &full[stage], kc * GEMM_BK, 0, brow);
-                        }
-                    } else if (it < main_iters) {
-                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                        const int dh = tap / p.kw - p.pad, dw = tap % p.kw - p.pad;
-                        tma_load_4d(a_dst, &tmA, &full[stage], kc * GEMM_BK, w0 + dw, h0 + dh, b0);
-                        tma_load_3d(b_dst, &tmB, &full[stage], kc * GEMM_BK, tap, n0);
-                        if (GEGLU)
-                            tma_load_3d(b_dst + bn_out * 128, &tmB, &full[stage], kc * GEMM_BK, tap, p.N + n0);
-                    } else {
-                        const int kc = it - main_iters;
-                        tma_load_4d(a_dst, &tmA2, &full[stage], kc * GEMM_BK, w0, h0, b0);
-                        tma_load_3d(b_dst, &tmB2, &full[stage], kc * GEMM_BK, 0, n0);
+                const int w0 = tw * p.bw - pad, h0 = th * p.bh - pad, b0 = tb * p.nb, n0 = nt * bn_out;
+                // this CTA's B rows. PAIR: GEGLU -> CTA 0 value rows, CTA 1 gate rows; else the two N halves
+                const int brow = !PAIR ? n0 : GEGLU ? (leader ? n0 : p.N + n0) : n0 + static_cast<int>(rank) * (p.BN >> 1);
+                const int it0 = ks * kps, it1 = min(k_iters, it0 + kps);
+                int tap = 0, kc = 0, kx = 0, ky = 0;
+                if (it0 > 0 && it0 < main_iters) {
+                    tap = it0 / kchunks; kc = it0 - tap * kchunks;
+                    ky = tap / kw; kx = tap - ky * kw;
+                }
+                int c0 = kc * GEMM_BK;
+                const int it_main = min(it1, main_iters);
+                int it = it0;
+                for (; it < it_main; ++it) {
+                    mbar_wait_a(eb, phase ^ 1);
+                    if (elect_one()) {
+                        if (!PAIR || leader) mbar_expect_tx_a(fb, tx_bytes);  // PAIR: both CTAs' bytes land on CTA 0's barrier
+                        tma_load_4d_a<PAIR>(a_dst, &tmA, fb, c0, w0 + kx, h0 + ky, b0);
+                        tma_load_3d_a<PAIR>(a_dst + GEMM_A_BYTES, &tmB, fb, c0, tap, brow);
+                        if (GEGLU && !PAIR) tma_load_3d_a<false>(a_dst + gate_off, &tmB, fb, c0, tap, p.N + n0);
                     }
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    __syncwarp();
+                    c0 += GEMM_BK;
+                    if (++kc == kchunks) {
+                        kc = 0; c0 = 0; ++tap;
+                        if (++kx == kw) { kx = 0; ++ky; }
+                    }
+                    a_dst += stage_bytes; fb += 8; eb += 8;
+                    if (++stage == nstages) { stage = 0; phase ^= 1; a_dst = smem0; fb = full0; eb = empty0; }
+                }
+                c0 = (max(it0, main_iters) - main_iters) * GEMM_BK;
+                for (; it < it1; ++it) {  // second operand pair (fused 1x1 skip convolution)
+                    mbar_wait_a(eb, phase ^ 1);
+                    if (elect_one()) {
+                        if (!PAIR || leader) mbar_expect_tx_a(fb, tx_bytes);
+                        tma_load_4d_a<PAIR>(a_dst, &tmA2, fb, c0, w0 + pad, h0 + pad, b0);
+                        tma_load_3d_a<PAIR>(a_dst + GEMM_A_BYTES, &tmB2, fb, c0, 0, brow);
+                    }
+                    __syncwarp();
+                    c0 += GEMM_BK;
+                    a_dst += stage_bytes; fb += 8; eb += 8;
+                    if (++stage == nstages) { stage = 0; phase ^= 1; a_dst = smem0; fb = full0; eb = empty0; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ------------------------------------------------ MMA issuer (single thread; CTA 0 issues for the pair)
+        if (leader) {
+            // ------------------------------------------------ MMA issuer (whole warp loops, one elected lane issues; CTA 0
+            // issues for the pair)
+            const int kps = p.kiters_per_split;
+            const uint32_t idesc = p.idesc;
+            const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull), tempty0 = smem_u32(tempty);
+            // descriptors differ between stages only in the 14-bit start-address field (16-byte units)
+            const uint64_t a_desc0 = umma_desc_kmajor_sw128(smem_u32(smem));
+            const uint64_t b_desc0 = umma_desc_kmajor_sw128(smem_u32(smem) + GEMM_A_BYTES);
+            const uint32_t stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, fb = full0, eb = empty0, desc_off = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
-                int mt, ks, nt;
-                decode(tile, mt, ks, nt);
-                const int it0 = ks * p.kiters_per_split, it1 = min(k_iters, it0 + p.kiters_per_split);
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                const int ks = (tile / m_units) % p.splits;
+                const int it0 = ks * kps, it1 = min(k_iters, it0 + kps);
+                mbar_wait_a(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
+                uint32_t accum = 0;
                 for (int it = it0; it < it1; ++it) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait_a(fb, phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-                    const uint32_t b_addr = a_addr + GEMM_A_BYTES;
+                    const uint64_t a_desc = a_desc0 + desc_off, b_desc = b_desc0 + desc_off;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        if (PAIR)
-                            umma_f16_2cta(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                                          p.idesc, (it > it0 || k > 0) ? 1u : 0u);
-                        else
-                            umma_f16(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                                     p.idesc, (it > it0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            if (PAIR) umma_f16_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (accum | k) ? 1u : 0u);
+                            else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (accum | k) ? 1u : 0u);
+                        }
+                        umma_commit_a<PAIR>(eb);  // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+                        // accumulator ready: committed by the SAME lane that issued the MMAs (commit tracks the issuing thread)
+                        if (it + 1 == it1) umma_commit_a<PAIR>(tfull0 + 8 * acc);
                     }
-                    // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-                    if (PAIR) umma_commit_2cta(&empty[stage]); else umma_commit(&empty[stage]);
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    __syncwarp();
+                    accum = 1;
+                    fb += 8; eb += 8; desc_off += stage_step;
+                    if (++stage == nstages) { stage = 0; phase ^= 1; fb = full0; eb = empty0; desc_off = 0; }
                 }
-                if (PAIR) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
