@@ -552,8 +552,19 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     }
     const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int k_iters = p.taps * p.kchunks + p.kchunks2;
-    // ---- pick the N tile and the K split with a per-tile cycle model: a tile costs
-    // max(MMA issue, operand bytes through the SM's L2 port, epilogue) and the launch costs waves x tile.
+    // ---- 2-CTA pairs (cta_group::2): every SM ingests half of the B tile; needs an even split of N and no split-K
+    static int pair_env = -1;
+    if (pair_env < 0) {
+        const char* e = getenv("CTRLORA_GEMM_PAIR");
+        pair_env = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;  // 0: never, 1: per-shape policy, 2: wherever legal
+    }
+    // Measured (profiles/README.md): pairs win where the k loop dominates (3x3 convs: -10..-30 %), lose on short-K 1x1 /
+    // GEGLU tiles whose time is the epilogue (the pair's two epilogues serialise behind one accumulator hand-off).
+    const bool pair_shape = pair_env == 2 || (p.taps > 1 && !p.geglu && k_iters >= 24);
+    const bool pair_ok = pair_env && pair_shape && g_num_sms >= 2 && a->force_single_cta == 0;
+    // ---- pick the N tile and the K split with a per-tile cycle model, in cycles at the ~1.45 GHz the
+    // part holds under tensor load: a k-step costs max(MMA = 2 x BN, operand bytes / 69 B/clk (~100 GB/s per SM, the
+    // measured L2->SM share with all SMs pulling)); a launch costs waves x (k-steps + exposed epilogue).
     int bn_out = a->block_n, splits = a->split_k > 0 ? a->split_k : 1;
     if (bn_out <= 0) {
         double best_cost = -1;
@@ -578,10 +589,12 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
                 const int kps = (k_iters + S - 1) / S;
                 if (S > 1 && kps < 4 && a->split_k <= 0) break;
                 const int s_eff = (k_iters + kps - 1) / kps;
-                const long tiles = tiles_mn * s_eff;
-                const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+                const bool cpair = pair_ok && s_eff == 1 && bnt % 32 == 0;
+                const long tiles = cpair ? (long)((m_tiles + 1) / 2) * nt : tiles_mn * s_eff;
+                const long slots = cpair ? g_num_sms / 2 : g_num_sms;
+                const long waves = (tiles + slots - 1) / slots;
                 const double t_mma = kps * 4.0 * (bnt / 2 > 32 ? bnt / 2 : 32);
-                const double t_load = kps * (double)(GEMM_A_BYTES + bnt * 128) / 72.0;
+                const double t_load = kps * (double)(GEMM_A_BYTES + (cpair ? bnt / 2 : bnt) * 128) / 69.0;
                 const double t_epi = (cand / 32 + 1) * 350.0;
                 double t_tile = (t_mma > t_load ? t_mma : t_load);
                 if (t_epi > t_tile) t_tile = t_epi;
@@ -606,13 +619,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         p.ws = a->splitk_ws;
         p.counters = a->splitk_counters;
     }
-    // ---- 2-CTA pairs (cta_group::2): every SM ingests half of the B tile; needs an even split of N and no split-K
-    static int pair_env = -1;
-    if (pair_env < 0) {
-        const char* e = getenv("CTRLORA_GEMM_PAIR");
-        pair_env = (e && e[0] == '0') ? 0 : 1;
-    }
-    const bool pair = pair_env && p.splits == 1 && (p.BN % 32 == 0) && g_num_sms >= 2 && a->force_single_cta == 0;
+    const bool pair = pair_ok && p.splits == 1 && (p.BN % 32 == 0);
     const int b_rows = pair ? p.BN / 2 : p.BN;  // B rows held by one CTA
     p.stage_bytes = GEMM_A_BYTES + ((b_rows * 128 + 1023) / 1024) * 1024;
     p.stages = GEMM_SMEM_DATA / p.stage_bytes;

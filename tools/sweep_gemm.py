@@ -12,6 +12,7 @@ from tools.profile_kernels import rnd, timeit  # noqa: E402
 SHAPES = [  # B, H, W, C, N, ksize
     (8, 8, 8, 1280, 1280, 3), (8, 16, 16, 1280, 1280, 3), (8, 16, 16, 1280, 1280, 1), (8, 32, 32, 640, 640, 1),
     (8, 64, 64, 320, 320, 1), (8, 8, 8, 1280, 1280, 1), (8, 16, 16, 2560, 1280, 3), (8, 32, 32, 640, 640, 3),
+    (8, 64, 64, 320, 320, 3), (8, 32, 32, 1920, 640, 3), (8, 64, 64, 960, 320, 3), (8, 64, 64, 640, 320, 3),
 ]
 if __name__ == "__main__":
     for (b, h, w, c, n, ks) in SHAPES:
