@@ -133,6 +133,8 @@ template <bool GEGLU, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCt,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRt,
                     const __grid_constant__ GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,6 +145,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tempty = bars + 2 * GEMM_MAX_STAGES + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_MAX_STAGES + 4);
     volatile int* last_flag = reinterpret_cast<volatile int*>(bars + 2 * GEMM_MAX_STAGES + 5);
+    uint64_t* rfull = bars + 2 * GEMM_MAX_STAGES + 6;    // residual tile landed in staging buffer i (TMA epilogue)
+    uint64_t* rempty = bars + 2 * GEMM_MAX_STAGES + 8;   // staging buffer i drained by all epilogue warps
     float* sbias_all = reinterpret_cast<float*>(smem + GEMM_SMEM_DATA + 512);  // [2 tile parities][value 256 | gate 256]
 
     pdl_launch_dependents();
@@ -157,6 +161,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.epi_tma) {
+            tma_prefetch_desc(&tmC);
+            tma_prefetch_desc(&tmCt);
+            if (p.epi_res) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmRt); }
+        }
         if (p.kchunks2 > 0) {
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmB2);
@@ -170,6 +179,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);
+            mbar_init(&rfull[i], 1);
+            mbar_init(&rempty[i], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -213,8 +224,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t stage_bytes = static_cast<uint32_t>(p.stage_bytes);
             const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
             const uint32_t gate_off = GEMM_A_BYTES + static_cast<uint32_t>(bn_out) * 128;
-            int stage = 0;
-            uint32_t phase = 0, a_dst = smem0, fb = full0, eb = empty0;
+            const uint32_t rfull0 = smem_u32(rfull), rempty0 = smem_u32(rempty);
+            int stage = 0, rbuf = 0;
+            uint32_t phase = 0, a_dst = smem0, fb = full0, eb = empty0, rphase = 0;
             for (int tile = tile_first; tile < total_tiles; tile += tile_stride) {
                 int mt, ks, nt;
                 decode(tile, mt, ks, nt);
@@ -260,6 +272,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     c0 += GEMM_BK;
                     a_dst += stage_bytes; fb += 8; eb += 8;
                     if (++stage == nstages) { stage = 0; phase ^= 1; a_dst = smem0; fb = full0; eb = empty0; }
+                }
+                if (p.epi_res) {
+                    // residual tile of THIS tile -> staging buffer; it is needed only when the tile's MMAs are done
+                    mbar_wait_a(rempty0 + 8 * rbuf, rphase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t rb = rfull0 + 8 * rbuf;
+                        const uint32_t dst = smem0 + p.epi_off + rbuf * p.epi_buf_bytes;
+                        mbar_expect_tx_a(rb, GEMM_BM * bn_out * 2);
+                        for (int b = 0; b < p.epi_nfull; ++b)
+                            tma_load_4d_a<false>(dst + b * 16384, &tmR, rb, n0 + 64 * b, w0 + pad, h0 + pad, b0);
+                        if (p.epi_tail)
+                            tma_load_4d_a<false>(dst + p.epi_nfull * 16384, &tmRt, rb, n0 + 64 * p.epi_nfull, w0 + pad, h0 + pad, b0);
+                    }
+                    __syncwarp();
+                    if (++rbuf == p.epi_nbuf) { rbuf = 0; rphase ^= 1; }
                 }
             }
         }
@@ -316,7 +343,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int iw = r % p.bw, ih = (r / p.bw) % p.bh, ib = r / (p.bw * p.bh);
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint4 rres[3][4];
         int tile_iter = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_stride, ++tile_iter) {
             int mt, ks, nt;
@@ -341,39 +367,115 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 sb[e] = bv;
                 if (GEGLU) sb[256 + e] = bg;
             }
-            // ---- residual: registers hold THIS tile's chunks (loaded while the previous tile was being finished)
-            const bool res16 = !GEGLU && p.residual && !p.residual_f32 && (p.ldr & 7) == 0 && p.splits == 1;
-            auto load_res = [&](uint4* dst, long long mm, int nn0, int c) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + mm * p.ldr + nn0 + c);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dst[q] = __ldg(rp + q);
-            };
-            if (res16 && tile_iter == 0 && row_ok) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int c = 32 * half + 64 * i;
-                    if (c + 32 <= bn_out && n0 + c + 32 <= p.N) load_res(rres[i], m, n0, c);
+            // ---- TMA epilogue: make sure this tile's staging buffer is free (our own bulk stores of `nbuf` tiles ago
+            // have finished reading it); with a residual the buffer is handed back to the producer warp instead
+            const int sbuf = p.epi_nbuf == 2 ? (tile_iter & 1) : 0;
+            const uint32_t sphase = p.epi_nbuf == 2 ? ((tile_iter >> 1) & 1) : (tile_iter & 1);
+            if (p.epi_tma) {
+                if (lane == 0) {
+                    if (p.epi_res) {
+                        if (tile_iter > 0) {
+                            bulk_wait_group_read<0>();
+                            mbar_arrive(&rempty[p.epi_nbuf == 2 ? ((tile_iter - 1) & 1) : 0]);
+                        }
+                    } else if (p.epi_nbuf == 2) {
+                        bulk_wait_group_read<1>();
+                    } else {
+                        bulk_wait_group_read<0>();
+                    }
                 }
-            }
-            // coordinates of this CTA's next tile (for the refill of the residual registers)
-            bool nrow_ok = false;
-            long long nm = 0;
-            int nn0 = 0;
-            if (res16 && tile + tile_stride < total_tiles) {
-                int mt2, ks2, nt2;
-                decode(tile + tile_stride, mt2, ks2, nt2);
-                const int tw2 = mt2 % p.tiles_w, th2 = (mt2 / p.tiles_w) % p.tiles_h, tb2 = mt2 / (p.tiles_w * p.tiles_h);
-                const int gw2 = tw2 * p.bw + iw, gh2 = th2 * p.bh + ih, gb2 = tb2 * p.nb + ib;
-                nrow_ok = gw2 < p.W && gh2 < p.H && gb2 < p.Bn;
-                nm = (static_cast<long long>(gb2) * p.H + gh2) * p.W + gw2;
-                nn0 = nt2 * bn_out;
+                __syncwarp();
             }
             asm volatile("bar.sync 2, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");  // bias staged
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * 256 + (static_cast<uint32_t>(lane_grp * 32) << 16);
 
-            if (p.splits == 1) {
+            if (p.epi_tma) {
+                // ---- TMEM -> registers -> swizzled staging (in place over the residual tile) -> TMA store per warp
+                if (p.epi_res) mbar_wait(&rfull[sbuf], sphase);
+                uint8_t* stg = smem + p.epi_off + sbuf * p.epi_buf_bytes;
+                const int nblk = p.epi_nfull + p.epi_tail;
+                for (int b = half; b < nblk; b += 2) {  // the two warps of a lane group take alternate 64-column blocks
+                    const bool tail = b == p.epi_nfull;
+                    uint8_t* rowp = stg + b * 16384 + (tail ? r * 64 : r * 128);
+                    const int sw = tail ? ((r >> 1) & 3) : (r & 7);
+                    for (int cc = 0; cc < (tail ? 1 : 2); ++cc) {
+                        const int c = 64 * b + 32 * cc;
+                        uint32_t raw[32];
+                        float v[32];
+                        tmem_ld_32x32(t_row + c, raw);
+                        if (GEGLU) {
+                            uint32_t graw[32];
+                            tmem_ld_32x32(t_row + bn_out + c, graw);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+                                const float4 g4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * q);
+                                v[4 * q] = (__uint_as_float(raw[4 * q]) + b4.x) * gelu_erf_f(__uint_as_float(graw[4 * q]) + g4.x);
+                                v[4 * q + 1] = (__uint_as_float(raw[4 * q + 1]) + b4.y) * gelu_erf_f(__uint_as_float(graw[4 * q + 1]) + g4.y);
+                                v[4 * q + 2] = (__uint_as_float(raw[4 * q + 2]) + b4.z) * gelu_erf_f(__uint_as_float(graw[4 * q + 2]) + g4.z);
+                                v[4 * q + 3] = (__uint_as_float(raw[4 * q + 3]) + b4.w) * gelu_erf_f(__uint_as_float(graw[4 * q + 3]) + g4.w);
+                            }
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+                                v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x;
+                                v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
+                                v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z;
+                                v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b4.w;
+                            }
+                        }
+                        if (p.rowbias && row_ok) {
+                            const float* rb = p.rowbias + static_cast<long long>(img) * p.rowbias_ld + n0 + c;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + c + j < p.N) v[j] += __ldg(rb + j);
+                        }
+                        if (p.out_scale != 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4* sp = reinterpret_cast<uint4*>(rowp + (((4 * cc + q) ^ sw) << 4));
+                            if (p.epi_res) {
+                                const uint4 x = *sp;
+                                const __half2* h = reinterpret_cast<const __half2*>(&x);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __half22float2(h[e]);
+                                    v[q * 8 + e * 2] += f.x;
+                                    v[q * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                            uint4 u;
+                            u.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]);
+                            u.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
+                            u.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
+                            u.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
+                            *sp = u;
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the bulk-store engine
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_leader(&tempty[acc]); else mbar_arrive(&tempty[acc]);
+                    const int r0 = lane_grp * 32;  // this warp's 32 rows are a rectangular sub-box of the tile's pixel box
+                    const int cw = tw * p.bw + r0 % p.bw, ch = th * p.bh + (r0 / p.bw) % p.bh, cb = tb * p.nb + r0 / (p.bw * p.bh);
+                    const uint32_t s0 = smem_u32(stg);
+                    for (int b = half; b < nblk; b += 2) {
+                        if (b == p.epi_nfull) tma_store_4d(&tmCt, s0 + b * 16384 + lane_grp * 2048, n0 + 64 * b, cw, ch, cb);
+                        else tma_store_4d(&tmC, s0 + b * 16384 + lane_grp * 4096, n0 + 64 * b, cw, ch, cb);
+                    }
+                    bulk_commit_group();
+                }
+            } else if (p.splits == 1) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {  // bn_out <= 256: at most four 32-column chunks per warp
                     const int c = 32 * half + 64 * i;
@@ -392,10 +494,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                    const bool pre = res16 && row_ok && i < 3 && (c + 32 <= bn_out) && (n0 + c + 32 <= p.N);
-                    epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, sb, pre ? rres[i < 3 ? i : 0] : nullptr);
-                    // refill the slot with the same chunk of this CTA's NEXT tile: a whole tile of lead time
-                    if (res16 && nrow_ok && i < 3 && (c + 32 <= bn_out) && (nn0 + c + 32 <= p.N)) load_res(rres[i < 3 ? i : 0], nm, nn0, c);
+                    epilogue_chunk<GEGLU>(p, v, g, c, bn_out, n0, row_ok, m, img, tok, sb);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -459,6 +558,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (p.epi_tma && lane == 0) bulk_wait_group<0>();  // staging must outlive the bulk stores that read it
     }
     tc_fence_before();
     __syncthreads();
@@ -489,8 +589,14 @@ PFN_tmapEncodeTiled get_tmap_encoder() {
 }
 
 // fp16 tensor map with SWIZZLE_128B, zero OOB fill; dims innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap_f16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, CUtensorMapSwizzle swz);
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+    return make_tmap_f16_sw(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_tmap_f16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box, CUtensorMapSwizzle swz) {
     PFN_tmapEncodeTiled enc = get_tmap_encoder();
     if (!enc) return CTRLORA_ERR_TMAP;
     cuuint64_t gdim[5], gstr[4];
@@ -498,7 +604,7 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "ctrlora: cuTensorMapEncodeTiled failed (%d) rank %d dims", (int)r, rank);
@@ -558,13 +664,23 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         const char* e = getenv("CTRLORA_GEMM_PAIR");
         pair_env = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;  // 0: never, 1: per-shape policy, 2: wherever legal
     }
-    // Measured (profiles/README.md): pairs win where the k loop dominates (3x3 convs: -10..-30 %), lose on short-K 1x1 /
-    // GEGLU tiles whose time is the epilogue (the pair's two epilogues serialise behind one accumulator hand-off).
-    const bool pair_shape = pair_env == 2 || (p.taps > 1 && !p.geglu && k_iters >= 24);
+    // Measured (profiles/README.md): pairs win where the k loop dominates (3x3 convs and K >= 1024 linears: -10..-30 %),
+    // lose on short-K 1x1 / GEGLU tiles whose time is the epilogue.
+    const bool pair_shape = pair_env == 2 || (!p.geglu && k_iters >= (p.taps > 1 ? 24 : 16));
     const bool pair_ok = pair_env && pair_shape && g_num_sms >= 2 && a->force_single_cta == 0;
     // ---- pick the N tile and the K split with a per-tile cycle model, in cycles at the ~1.45 GHz the
     // part holds under tensor load: a k-step costs max(MMA = 2 x BN, operand bytes / 69 B/clk (~100 GB/s per SM, the
     // measured L2->SM share with all SMs pulling)); a launch costs waves x (k-steps + exposed epilogue).
+    static int epi_env = -1;
+    if (epi_env < 0) {
+        const char* e = getenv("CTRLORA_GEMM_EPI");
+        epi_env = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;  // 0: direct only, 1: per-shape policy, 2: wherever legal
+    }
+    // TMA-staged epilogue (see below): legal for plain fp16 row-major outputs; wanted where the k loop is short
+    const bool epi_legal = !a->out_f32 && a->split_k <= 1 && a->seg_width == 0 && !a->transposed[0] && !a->dup_out &&
+                           a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out[0]) & 15) == 0 &&
+                           (!a->residual || (!a->residual_f32 && a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0));
+    const bool epi_wanted = epi_legal && (epi_env == 2 || (epi_env == 1 && k_iters <= 32));
     int bn_out = a->block_n, splits = a->split_k > 0 ? a->split_k : 1;
     if (bn_out <= 0) {
         double best_cost = -1;
@@ -572,6 +688,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16};
         for (int cand = max_out; cand >= 16; cand -= 16) {
             if (a->seg_width > 0 && a->seg_width % cand != 0) continue;
+            if (epi_wanted && cand % 32 != 0) continue;  // the staged epilogue works in 64- and 32-column blocks
             const int bnt = p.geglu ? 2 * cand : cand;
             const int nt = (p.N + cand - 1) / cand;
             const long tiles_mn = (long)m_tiles * nt;
@@ -622,7 +739,25 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     const bool pair = pair_ok && p.splits == 1 && (p.BN % 32 == 0);
     const int b_rows = pair ? p.BN / 2 : p.BN;  // B rows held by one CTA
     p.stage_bytes = GEMM_A_BYTES + ((b_rows * 128 + 1023) / 1024) * 1024;
-    p.stages = GEMM_SMEM_DATA / p.stage_bytes;
+    // ---- epilogue flavour: short-K shapes are epilogue-bound (profiles/README.md: per-row 16-byte global accesses of the
+    // direct epilogue cost ~8 us per 128x160 tile), so they stage the tile in swizzled shared memory and let TMA do the
+    // (coalesced, asynchronous) residual load and output store. Long-K shapes keep the deeper operand ring instead.
+    int ring_bytes = GEMM_SMEM_DATA;
+    {
+        if (epi_wanted && p.splits == 1 && bn_out % 32 == 0) {
+            const int nfull = bn_out / 64, tail = (bn_out % 64) ? 1 : 0;
+            const int buf_bytes = nfull * 16384 + tail * 8192;
+            int nbuf = 2;
+            if ((GEMM_SMEM_DATA - 2 * buf_bytes) / p.stage_bytes < 3) nbuf = 1;
+            if ((GEMM_SMEM_DATA - nbuf * buf_bytes) / p.stage_bytes >= 3) {
+                p.epi_tma = 1; p.epi_nbuf = nbuf; p.epi_res = a->residual ? 1 : 0;
+                p.epi_nfull = nfull; p.epi_tail = tail; p.epi_buf_bytes = buf_bytes;
+                p.epi_off = GEMM_SMEM_DATA - nbuf * buf_bytes;
+                ring_bytes = p.epi_off;
+            }
+        }
+    }
+    p.stages = ring_bytes / p.stage_bytes;
     if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
     p.idesc = umma_idesc_f16(pair ? 2 * GEMM_BM : GEMM_BM, p.BN, 0);
     for (int i = 0; i < 3; ++i) { p.out[i] = a->out[i]; p.transposed[i] = a->transposed[i]; }
@@ -667,6 +802,30 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         tmA2 = tmA;
         tmB2 = tmB;
     }
+    CUtensorMap tmC = tmA, tmCt = tmA, tmR = tmA, tmRt = tmA;
+    if (p.epi_tma) {
+        // output: per-warp stores of a 32-row sub-box of the tile's (bw, bh, nb) pixel box; residual: whole-tile loads
+        const int sw = p.bw < 32 ? p.bw : 32;
+        const int sh = p.bh < 32 / sw ? p.bh : 32 / sw;
+        const int sb = 32 / (sw * sh);
+        uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
+        uint64_t str[3] = {(uint64_t)a->ldc * 2, (uint64_t)a->ldc * 2 * p.W, (uint64_t)a->ldc * 2 * p.W * p.H};
+        uint32_t box[4] = {64, (uint32_t)sw, (uint32_t)sh, (uint32_t)sb};
+        int rc = make_tmap_f16_sw(&tmC, a->out[0], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        box[0] = 32;
+        rc = make_tmap_f16_sw(&tmCt, a->out[0], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        if (p.epi_res) {
+            uint64_t rstr[3] = {(uint64_t)a->ldr * 2, (uint64_t)a->ldr * 2 * p.W, (uint64_t)a->ldr * 2 * p.W * p.H};
+            uint32_t rbox[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.nb};
+            rc = make_tmap_f16_sw(&tmR, a->residual, 4, dims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+            rbox[0] = 32;
+            rc = make_tmap_f16_sw(&tmRt, a->residual, 4, dims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        }
+    }
     if (!g_attr_set) {
         if (cudaFuncSetAttribute(gemm_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(gemm_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
@@ -681,15 +840,15 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         int clusters = g_num_sms / 2;
         if (units < clusters) clusters = units;
         const dim3 grid2(2 * clusters), block(GEMM_THREADS);
-        lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, p)
-                      : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, p);
+        lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p)
+                      : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p);
     } else {
         const int total = m_tiles * p.n_tiles * p.splits;
         const int grid = total < g_num_sms ? total : g_num_sms;
         lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                   stream, tmA, tmB, tmA2, tmB2, p)
+                                   stream, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p)
                       : launch_pdl(gemm_tcgen05_kernel<false, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                   stream, tmA, tmB, tmA2, tmB2, p);
+                                   stream, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p);
     }
     if (lrc != cudaSuccess) return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;

@@ -48,6 +48,11 @@ struct GemmKParams {
     __half* dup_out;               // transposed segments are ALSO stored row-major here (training keeps natural V)
     int dup_ld;
     int bf16;
+    // TMA-staged epilogue (short-K shapes): tile -> swizzled shared staging -> cp.async.bulk.tensor stores; the fp16
+    // residual tile is TMA-loaded into the same staging buffer one tile ahead and updated in place.
+    int epi_tma, epi_nbuf, epi_res;
+    int epi_off, epi_buf_bytes;     // staging buffers live at the top of the ring area
+    int epi_nfull, epi_tail;        // 64-column SWIZZLE_128B blocks (16 KiB each) + optional 32-column SWIZZLE_64B tail (8 KiB)
 };
 
 }  // namespace ctrl
