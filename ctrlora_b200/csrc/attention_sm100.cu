@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "ctrlora_b200.h"
 #include "gemm_sm100.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace ctrl {
@@ -309,6 +310,345 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
 }
 
+// =====================================================================================================================
+// Streaming kernel for long key sequences (Nk > 256, d <= 80): the 64x64 / 32x32 self-attentions, i.e. almost all of the
+// attention time.  Differences from the MULTI path above (measured 35 % of the MUFU bound, profiles/README.md):
+//   * O (and the row sums l) stay in TMEM across KV tiles: the P V product accumulates; nothing is folded through
+//     registers per tile.  The softmax reference m_ref is LAZY: a tile only moves it (and rescales O, l in TMEM) when
+//     its row maximum exceeds m_ref by more than 2^TAU -- after the first tiles that is rare.  P <= 2^TAU stays far
+//     inside fp16 range and the result is algebraically the same softmax.
+//   * one pass over S per tile (TMEM read once, exp2 straight away against m_ref); a warp that finds a violating row
+//     redoes its 32 rows (slow path).
+//   * when d is not a multiple of 16 the zero padding row d of the V^T tile is overwritten with 1.0, so column d of
+//     O IS the row sum (no separate P x ones product).
+//   * the MMA warp issues S(j+1) BEFORE P V(j): the next tile's logits are ready while P V(j) still runs.
+constexpr float ATT_TAU = 8.0f;
+
+template <int DPAD>
+struct StreamSmem {
+    static constexpr int BKV = 128;
+    static constexpr int NKC = (DPAD + 63) / 64;
+    static constexpr int Q_BYTES = NKC * 128 * 128;
+    static constexpr int K_BYTES = NKC * BKV * 128;
+    static constexpr int V_CHUNK = DPAD * 128;
+    static constexpr int V_BYTES = (BKV / 64) * V_CHUNK;
+    static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+    static constexpr int P_OFF = Q_BYTES + 2 * STAGE_BYTES;
+    static constexpr int P_BYTES = (BKV / 64) * 128 * 128;
+    static constexpr int ONES_OFF = P_OFF + P_BYTES;
+    static constexpr int BAR_OFF = ONES_OFF + 2048;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 128;
+    static constexpr int TMEM_COLS = 256;  // S 128 | O DPAD | l 16
+};
+
+// P = exp2(s * sl2 + neg) for one 32-column chunk of one row; tmax tracks the raw row maximum over valid columns.
+template <bool MASK>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&raw)[32], float sl2, float neg, int c, int kv_valid,
+                                              uint32_t (&packed)[16], float& tmax) {
+    if (!MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            tmax = max3f(tmax, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, neg));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), sl2, neg));
+            packed[i >> 1] = pack_half2(p0, p1);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const bool v0 = c + i < kv_valid, v1 = c + i + 1 < kv_valid;
+            if (v0) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+            if (v1) tmax = fmaxf(tmax, __uint_as_float(raw[i + 1]));
+            const float p0 = v0 ? fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, neg)) : 0.f;
+            const float p1 = v1 ? fast_exp2(fmaf(__uint_as_float(raw[i + 1]), sl2, neg)) : 0.f;
+            packed[i >> 1] = pack_half2(p0, p1);
+        }
+    }
+}
+__device__ __forceinline__ void store_p_chunk(uint8_t* sP, int r, int c, const uint32_t (&packed)[16]) {
+    uint8_t* chunk = sP + (c >> 6) * 128 * 128 + r * 128;
+    const int u0 = (c & 63) >> 3;  // first 16-byte unit of this 32-column group within the 128 B row
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) =
+            make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+}
+
+template <int DPAD>
+__global__ void __launch_bounds__(ATT_THREADS, DPAD <= 48 ? 2 : 1)
+attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+    using L = StreamSmem<DPAD>;
+    constexpr int BKV = L::BKV;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint8_t* sOnes = smem + L::ONES_OFF;
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;   // [2]
+    uint64_t* kv_empty = bars + 3;  // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_full = bars + 6;
+    uint64_t* pv_full = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    const bool ones_row = p.d < p.d16;  // column d of O doubles as the row sum
+
+    uint8_t* sQ = smem;
+    auto sK = [&](int stage) { return smem + L::Q_BYTES + stage * L::STAGE_BYTES; };
+    auto sV = [&](int stage) { return smem + L::Q_BYTES + stage * L::STAGE_BYTES + L::K_BYTES; };
+    uint8_t* sP = smem + L::P_OFF;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 5 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(pv_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+    if (threadIdx.x < 128)  // 2 KiB of 1.0h (P x ones when there is no spare V^T row)
+        reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tmem_s = tmem_base;               // [0, 128)
+    const uint32_t tmem_o = tmem_base + BKV;         // [128, 128 + DPAD)
+    const uint32_t tmem_l = tmem_o + DPAD;           // [128 + DPAD, +16): P x ones (only without the ones row)
+    const int n_tiles = p.n_kv_tiles;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            mbar_expect_tx(q_full, p.nkc * 128 * 128);
+            for (int kc = 0; kc < p.nkc; ++kc) tma_load_4d(sQ + kc * 128 * 128, &tmQ, q_full, kc * 64, head, q0, img);
+            const uint32_t tx = p.nkc * BKV * 128 + (BKV / 64) * p.d16 * 128;
+            for (int j = 0; j < n_tiles; ++j) {
+                const int stage = j & 1;
+                if (j >= 2) mbar_wait(&kv_empty[stage], ((j >> 1) - 1) & 1);
+                mbar_expect_tx(&kv_full[stage], tx);
+                for (int kc = 0; kc < p.nkc; ++kc)
+                    tma_load_4d(sK(stage) + kc * BKV * 128, &tmK, &kv_full[stage], kc * 64, head, j * BKV, img);
+                for (int c = 0; c < BKV / 64; ++c)
+                    tma_load_4d(sV(stage) + c * L::V_CHUNK, &tmV, &kv_full[stage], j * BKV + c * 64, 0, head, img);
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------------------------------------------- MMA issuer (whole warp in the loop, one lane issues)
+        const int ksteps_s = (p.d + 15) / 16;
+        const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP), oa = smem_u32(sOnes);
+        // tile j's operands have landed: plant the ones row into its V^T chunks, then S(j) = Q K(j)^T
+        auto stage_ready_issue_s = [&](int j) {
+            const int stage = j & 1;
+            mbar_wait(&kv_full[stage], (j >> 1) & 1);
+            if (ones_row && lane < (BKV / 64) * 8) {
+                uint8_t* row = sV(stage) + (lane >> 3) * L::V_CHUNK + p.d * 128 + (lane & 7) * 16;
+                *reinterpret_cast<uint4*>(row) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(sK(stage));
+                for (int ks = 0; ks < ksteps_s; ++ks) {
+                    const uint32_t off_q = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    const uint32_t off_k = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
+                    umma_f16(tmem_s, umma_desc_kmajor_sw128(qa + off_q), umma_desc_kmajor_sw128(ka + off_k), p.idesc_s,
+                             ks != 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        stage_ready_issue_s(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int stage = j & 1;
+            mbar_wait(p_full, j & 1);  // P(j) is in shared memory and S(j) has been read out
+            if (j + 1 < n_tiles) stage_ready_issue_s(j + 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t va = smem_u32(sV(stage));
+                const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks) {
+                    const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    const uint32_t off_v = (ks >> 2) * L::V_CHUNK + (ks & 3) * 32;
+                    umma_f16(tmem_o, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
+                             (acc | ks) ? 1u : 0u);
+                }
+                if (!ones_row) {
+#pragma unroll
+                    for (int ks = 0; ks < BKV / 16; ++ks) {
+                        const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                        umma_f16(tmem_l, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(oa), p.idesc_l,
+                                 (acc | ks) ? 1u : 0u);
+                    }
+                }
+                umma_commit(pv_full);
+                umma_commit(&kv_empty[stage]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------- softmax + epilogue: thread == query row
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const float sl2 = p.scale_log2e;
+        float mr = -INFINITY;  // lazy reference maximum, already multiplied by scale * log2(e)
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv_valid = min(BKV, p.Nk - j * BKV);  // columns >= kv_valid are TMA zero fill: masked out
+            const bool full_tile = kv_valid == BKV;         // warp-uniform
+            float tmax = -INFINITY;
+            bool redo = (j == 0);
+            if (!redo) {
+                // ---- fast path: exponentials against the stale reference, one TMEM read
+                const float neg = -mr;
+                uint32_t ra[32], rb[32], packed[16];
+                tmem_ld_32x32(tmem_s + lane_off, ra);
+                tmem_ld_32x32(tmem_s + lane_off + 32, rb);
+                tmem_ld_wait();
+                if (full_tile) softmax_chunk<false>(ra, sl2, neg, 0, kv_valid, packed, tmax);
+                else softmax_chunk<true>(ra, sl2, neg, 0, kv_valid, packed, tmax);
+                tmem_ld_32x32(tmem_s + lane_off + 64, ra);
+                // P V(j-1) reads the P buffer and accumulates into O: both must be done before P(j) is written
+                mbar_wait(pv_full, (j - 1) & 1);
+                store_p_chunk(sP, r, 0, packed);
+                if (full_tile) softmax_chunk<false>(rb, sl2, neg, 32, kv_valid, packed, tmax);
+                else softmax_chunk<true>(rb, sl2, neg, 32, kv_valid, packed, tmax);
+                store_p_chunk(sP, r, 32, packed);
+                tmem_ld_wait();
+                tmem_ld_32x32(tmem_s + lane_off + 96, rb);
+                if (full_tile) softmax_chunk<false>(ra, sl2, neg, 64, kv_valid, packed, tmax);
+                else softmax_chunk<true>(ra, sl2, neg, 64, kv_valid, packed, tmax);
+                store_p_chunk(sP, r, 64, packed);
+                tmem_ld_wait();
+                if (full_tile) softmax_chunk<false>(rb, sl2, neg, 96, kv_valid, packed, tmax);
+                else softmax_chunk<true>(rb, sl2, neg, 96, kv_valid, packed, tmax);
+                store_p_chunk(sP, r, 96, packed);
+                redo = __any_sync(0xffffffffu, tmax * sl2 > mr + ATT_TAU);
+            } else {
+                // first tile: the row maximum is needed before anything else
+#pragma unroll 1
+                for (int c = 0; c < BKV; c += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_s + lane_off + c, raw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c + i < kv_valid) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+                }
+            }
+            if (redo) {
+                // ---- slow path (warp-uniform): move the reference of the violating rows, rescale O / l, redo this tile's P
+                const float tm = tmax * sl2;
+                const bool fix = tm > mr + ATT_TAU;            // first tile: mr = -inf -> every row
+                const float mr_new = fix ? tm : mr;
+                const float alpha = fix ? fast_exp2(mr - mr_new) : 1.0f;
+                mr = mr_new;
+                if (j > 0) {
+                    tc_fence_after();  // pv_full(j-1) was waited for above: O / l are quiescent
+                    const int ncols = ones_row ? DPAD : DPAD + 16;  // without the ones row, l sits right after O
+#pragma unroll 1
+                    for (int c = 0; c < ncols; c += 16) {
+                        uint32_t raw[16];
+                        tmem_ld_32x16(tmem_o + lane_off + c, raw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+                        tmem_st_32x16(tmem_o + lane_off + c, raw);
+                    }
+                    tmem_st_wait();
+                }
+                const float neg = -mr;
+                float dummy = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BKV; c += 32) {
+                    uint32_t raw[32], packed[16];
+                    tmem_ld_32x32(tmem_s + lane_off + c, raw);
+                    tmem_ld_wait();
+                    softmax_chunk<true>(raw, sl2, neg, c, kv_valid, packed, dummy);
+                    store_p_chunk(sP, r, c, packed);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- final: normalise, store
+        mbar_wait(pv_full, (n_tiles - 1) & 1);
+        tc_fence_after();
+        uint32_t lfin;
+        tmem_ld_32x1((ones_row ? tmem_o + p.d : tmem_l) + lane_off, lfin);
+        tmem_ld_wait();
+        const float l_tot = __uint_as_float(lfin);
+        const float inv_l = 1.0f / l_tot;
+        const bool row_ok = (q0 + r) < p.Nq;
+        if (p.lse && row_ok)
+            p.lse[(static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r] = mr + log2f(l_tot);
+        __half* orow = p.out + (static_cast<long long>(img) * p.Nq + q0 + r) * p.ldo + head * p.d;
+#pragma unroll
+        for (int c = 0; c < DPAD; c += 16) {
+            if (c < p.d) {  // warp-uniform
+                uint32_t raw[16];
+                tmem_ld_32x16(tmem_o + lane_off + c, raw);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        if (c + g * 8 < p.d) {
+                            uint4 u;
+                            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                h[e] = __floats2half2_rn(__uint_as_float(raw[g * 8 + 2 * e]) * inv_l,
+                                                         __uint_as_float(raw[g * 8 + 2 * e + 1]) * inv_l);
+                            *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+template <int DPAD>
+static int launch_attn_stream(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                              dim3 grid, cudaStream_t stream) {
+    using L = StreamSmem<DPAD>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attention_stream_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+            cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    if (launch_pdl(attention_stream_kernel<DPAD>, grid, dim3(ATT_THREADS), (size_t)L::TOTAL, stream, tq, tk, tv, p) !=
+        cudaSuccess)
+        return CTRLORA_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
 template <int DPAD, int BKV, bool MULTI>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                        cudaStream_t stream) {
@@ -374,6 +714,15 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
     }
     dim3 grid((nq + 127) / 128, heads, batch);
     if (multi) {
+        static int stream_env = -1;
+        if (stream_env < 0) {
+            const char* e = getenv("CTRLORA_ATTN_STREAM");
+            stream_env = (e && e[0] == '0') ? 0 : 1;  // 0: the older per-tile-fold kernel (kept for A/B measurements)
+        }
+        if (stream_env) {
+            if (d <= 48) return launch_attn_stream<48>(tq, tk, tv, p, grid, stream);
+            return launch_attn_stream<80>(tq, tk, tv, p, grid, stream);
+        }
         if (d <= 48) return launch_attn<48, 128, true>(tq, tk, tv, p, grid, stream);
         return launch_attn<80, 128, true>(tq, tk, tv, p, grid, stream);
     }
