@@ -88,7 +88,11 @@ struct DqSmem {
     static constexpr int Q_BYTES = NKC * 128 * 128;      // Q and dO: [nkc][128 q][128 B]
     static constexpr int KV_BYTES = NKC * BKV * 128;     // K and V:  [nkc][BKV keys][128 B]
     static constexpr int DS_BYTES = (BKV / 64) * 128 * 128 > 0 ? (BKV / 64) * 128 * 128 : 128 * 128;
-    static constexpr int OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_DS = OFF_V + KV_BYTES;
+    // K/V tiles are double-buffered where shared memory allows: the next tile's S / dP products are then issued before
+    // the current tile's dQ accumulation and the TMA latency disappears from the per-tile chain
+    static constexpr int STAGES = (2 * Q_BYTES + 4 * KV_BYTES + DS_BYTES <= 200 * 1024) ? 2 : 1;
+    static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+    static constexpr int OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_DS = OFF_K + STAGES * STAGE_BYTES;
     static constexpr int DATA = OFF_DS + DS_BYTES;
     static constexpr int TOTAL = DATA + 1024 + 128;
 };
@@ -102,16 +106,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sQ = smem, *sDO = smem + L::OFF_DO, *sK = smem + L::OFF_K, *sV = smem + L::OFF_V, *sDS = smem + L::OFF_DS;
+    uint8_t *sQ = smem, *sDO = smem + L::OFF_DO, *sDS = smem + L::OFF_DS;
+    constexpr int ST = L::STAGES;
+    auto sK = [&](int st) { return smem + L::OFF_K + st * L::STAGE_BYTES; };
+    auto sV = [&](int st) { return smem + L::OFF_V + st * L::STAGE_BYTES; };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA);
-    uint64_t *q_full = bars, *kv_full = bars + 1, *kv_free = bars + 2, *s_full = bars + 3, *ds_full = bars + 4, *acc_done = bars + 5;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t *q_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_free = bars + 3 /*[2]*/, *s_full = bars + 5, *ds_full = bars + 6,
+             *acc_done = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
     constexpr uint32_t TMEM_COLS = (2 * BKV + DPAD <= 256) ? 256 : 512;  // 256 columns: two CTAs share an SM's TMEM
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
     if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
     if (warp == 5 && lane == 0) {
-        mbar_init(q_full, 1); mbar_init(kv_full, 1); mbar_init(kv_free, 1); mbar_init(s_full, 1);
+        mbar_init(q_full, 1); mbar_init(s_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_free[i], 1); }
         mbar_init(ds_full, 128); mbar_init(acc_done, 1);
         fence_barrier_init();
     }
@@ -133,22 +142,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tma_load_4d(sDO + kc * 128 * 128, &tmDO, q_full, kc * 64, head, q0, img);
             }
             for (int j = 0; j < n_tiles; ++j) {
-                if (j > 0) mbar_wait(kv_free, (j - 1) & 1);
-                mbar_expect_tx(kv_full, 2 * p.nkc * BKV * 128);
+                const int st = j % ST;
+                if (j >= ST) mbar_wait(&kv_free[st], ((j / ST) - 1) & 1);
+                mbar_expect_tx(&kv_full[st], 2 * p.nkc * BKV * 128);
                 for (int kc = 0; kc < p.nkc; ++kc) {
-                    tma_load_4d(sK + kc * BKV * 128, &tmK, kv_full, kc * 64, head, j * BKV, img);
-                    tma_load_4d(sV + kc * BKV * 128, &tmV, kv_full, kc * 64, head, j * BKV, img);
+                    tma_load_4d(sK(st) + kc * BKV * 128, &tmK, &kv_full[st], kc * 64, head, j * BKV, img);
+                    tma_load_4d(sV(st) + kc * BKV * 128, &tmV, &kv_full[st], kc * 64, head, j * BKV, img);
                 }
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            mbar_wait(q_full, 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                mbar_wait(kv_full, j & 1);
-                if (j > 0) mbar_wait(ds_full, (j - 1) & 1);  // S / dP of the previous tile have been read out
-                tc_fence_after();
-                const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), ka = smem_u32(sK), va = smem_u32(sV);
+        // whole warp in the loop, one elected lane issues (uniform registers for the tcgen05 operands)
+        const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), dsa = smem_u32(sDS);
+        auto issue_s_dp = [&](int j) {  // S = Q K(j)^T, dP = dO V(j)^T
+            const int st = j % ST;
+            mbar_wait(&kv_full[st], (j / ST) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(sK(st)), va = smem_u32(sV(st));
                 for (int ks = 0; ks < ksteps_d; ++ks) {
                     const uint32_t oq = (ks >> 2) * 128 * 128 + (ks & 3) * 32, ok = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
                     umma_f16(tm_s, umma_desc_kmajor_sw128(qa + oq), umma_desc_kmajor_sw128(ka + ok), p.idesc_s, ks ? 1u : 0u);
@@ -158,18 +169,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     umma_f16(tm_dp, umma_desc_kmajor_sw128(doa + oq), umma_desc_kmajor_sw128(va + ok), p.idesc_s, ks ? 1u : 0u);
                 }
                 umma_commit(s_full);
-                mbar_wait(ds_full, j & 1);  // dS tile written
-                tc_fence_after();
-                const uint32_t dsa = smem_u32(sDS);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s_dp(0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % ST;
+            mbar_wait(ds_full, j & 1);  // dS(j) is in shared memory; S / dP(j) have been read out
+            if (ST == 2 && j + 1 < n_tiles) issue_s_dp(j + 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(sK(st));
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {  // contraction over the keys of this tile
                     const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
                     umma_f16(tm_dq, umma_desc_kmajor_sw128(dsa + oa), desc_mn_sw128(ka + ks * 2048, BKV * 128), p.idesc_acc,
                              (j > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(kv_free);  // K/V tile and the dS tile are free once these MMAs complete
+                umma_commit(&kv_free[st]);  // K/V stage and the dS tile are free once these MMAs complete
+                if (j + 1 == n_tiles) umma_commit(acc_done);
             }
-            umma_commit(acc_done);
+            __syncwarp();
+            if (ST == 1 && j + 1 < n_tiles) issue_s_dp(j + 1);
         }
     } else {
         const int r = warp * 32 + lane;
@@ -181,7 +203,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            if (j > 0) mbar_wait(kv_free, (j - 1) & 1);  // previous dQ MMAs have consumed the dS tile
             const int kv_valid = min(BKV, p.Nk - j * BKV);
 #pragma unroll 1
             for (int c = 0; c < BKV; c += 32) {
@@ -189,6 +210,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tmem_ld_32x32(tm_s + lane_off + c, sr);
                 tmem_ld_32x32(tm_dp + lane_off + c, dr);
                 tmem_ld_wait();
+                // the dQ MMAs of the previous tile read the dS buffer: they must be done before it is overwritten
+                if (c == 0 && j > 0) mbar_wait(&kv_free[(j - 1) % ST], ((j - 1) / ST) & 1);
                 if (kv_valid == BKV) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
@@ -253,9 +276,12 @@ struct DkvSmem {
     static constexpr int KV_BYTES = NKC * 128 * 128;   // K and V: [nkc][128 keys][128 B]
     static constexpr int Q_BYTES = NKC * BQ * 128;     // Q and dO: [nkc][BQ queries][128 B]
     static constexpr int PT_BYTES = (BQ / 64) * 128 * 128;  // P^T and dS^T: [BQ/64][128 keys][128 B]
-    static constexpr int OFF_V = KV_BYTES, OFF_Q = 2 * KV_BYTES, OFF_DO = OFF_Q + Q_BYTES, OFF_PT = OFF_DO + Q_BYTES,
+    // Q / dO tiles are double-buffered where shared memory allows (see DqSmem)
+    static constexpr int STAGES = (2 * KV_BYTES + 4 * Q_BYTES + 2 * PT_BYTES <= 200 * 1024) ? 2 : 1;
+    static constexpr int STAGE_BYTES = 2 * Q_BYTES;
+    static constexpr int OFF_V = KV_BYTES, OFF_Q = 2 * KV_BYTES, OFF_DO = OFF_Q + Q_BYTES, OFF_PT = OFF_Q + STAGES * STAGE_BYTES,
                          OFF_DST = OFF_PT + PT_BYTES, OFF_STAT = OFF_DST + PT_BYTES;
-    static constexpr int DATA = OFF_STAT + 2 * BQ * 4;
+    static constexpr int DATA = OFF_STAT + 2 * 2 * BQ * 4;  // lse / delta of the query tile, double-buffered
     static constexpr int BAR = (DATA + 127) / 128 * 128;
     static constexpr int TOTAL = BAR + 1024 + 128;
 };
@@ -269,19 +295,22 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sK = smem, *sV = smem + L::OFF_V, *sQ = smem + L::OFF_Q, *sDO = smem + L::OFF_DO, *sPT = smem + L::OFF_PT,
-            *sDST = smem + L::OFF_DST;
-    float* sLse = reinterpret_cast<float*>(smem + L::OFF_STAT);
-    float* sDel = sLse + BQ;
+    uint8_t *sK = smem, *sV = smem + L::OFF_V, *sPT = smem + L::OFF_PT, *sDST = smem + L::OFF_DST;
+    constexpr int ST = L::STAGES;
+    auto sQ = [&](int st) { return smem + L::OFF_Q + st * L::STAGE_BYTES; };
+    auto sDO = [&](int st) { return smem + L::OFF_DO + st * L::STAGE_BYTES; };
+    float* sStat = reinterpret_cast<float*>(smem + L::OFF_STAT);  // [2 buffers][lse BQ | delta BQ]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
-    uint64_t *kv_full = bars, *q_full = bars + 1, *q_free = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *acc_done = bars + 5;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t *kv_full = bars, *q_full = bars + 1 /*[2]*/, *q_free = bars + 3 /*[2]*/, *s_full = bars + 5, *p_full = bars + 6,
+             *acc_done = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
     constexpr uint32_t TMEM_COLS = (2 * BQ + 2 * DPAD <= 256) ? 256 : 512;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int k0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
     if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
     if (warp == 5 && lane == 0) {
-        mbar_init(kv_full, 1); mbar_init(q_full, 1); mbar_init(q_free, 1); mbar_init(s_full, 1);
+        mbar_init(kv_full, 1); mbar_init(s_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_free[i], 1); }
         mbar_init(p_full, 128); mbar_init(acc_done, 1);
         fence_barrier_init();
     }
@@ -303,34 +332,44 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tma_load_4d(sV + kc * 128 * 128, &tmV, kv_full, kc * 64, head, k0, img);
             }
             for (int i = 0; i < n_tiles; ++i) {
-                if (i > 0) mbar_wait(q_free, (i - 1) & 1);
-                mbar_expect_tx(q_full, 2 * p.nkc * BQ * 128);
+                const int st = i % ST;
+                if (i >= ST) mbar_wait(&q_free[st], ((i / ST) - 1) & 1);
+                mbar_expect_tx(&q_full[st], 2 * p.nkc * BQ * 128);
                 for (int kc = 0; kc < p.nkc; ++kc) {
-                    tma_load_4d(sQ + kc * BQ * 128, &tmQ, q_full, kc * 64, head, i * BQ, img);
-                    tma_load_4d(sDO + kc * BQ * 128, &tmDO, q_full, kc * 64, head, i * BQ, img);
+                    tma_load_4d(sQ(st) + kc * BQ * 128, &tmQ, &q_full[st], kc * 64, head, i * BQ, img);
+                    tma_load_4d(sDO(st) + kc * BQ * 128, &tmDO, &q_full[st], kc * 64, head, i * BQ, img);
                 }
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            mbar_wait(kv_full, 0);
-            for (int i = 0; i < n_tiles; ++i) {
-                mbar_wait(q_full, i & 1);
-                if (i > 0) mbar_wait(p_full, (i - 1) & 1);
-                tc_fence_after();
-                const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), ka = smem_u32(sK), va = smem_u32(sV);
-                for (int ks = 0; ks < ksteps_d; ++ks) {  // S^T = K Q^T
+        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), pta = smem_u32(sPT), dsta = smem_u32(sDST);
+        auto issue_s_dp = [&](int i) {  // S^T = K Q(i)^T, dP^T = V dO(i)^T
+            const int st = i % ST;
+            mbar_wait(&q_full[st], (i / ST) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qa = smem_u32(sQ(st)), doa = smem_u32(sDO(st));
+                for (int ks = 0; ks < ksteps_d; ++ks) {
                     const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
                     umma_f16(tm_s, umma_desc_kmajor_sw128(ka + ok), umma_desc_kmajor_sw128(qa + oq), p.idesc_s, ks ? 1u : 0u);
                 }
-                for (int ks = 0; ks < ksteps_d; ++ks) {  // dP^T = V dO^T
+                for (int ks = 0; ks < ksteps_d; ++ks) {
                     const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
                     umma_f16(tm_dp, umma_desc_kmajor_sw128(va + ok), umma_desc_kmajor_sw128(doa + oq), p.idesc_s, ks ? 1u : 0u);
                 }
                 umma_commit(s_full);
-                mbar_wait(p_full, i & 1);
-                tc_fence_after();
-                const uint32_t pta = smem_u32(sPT), dsta = smem_u32(sDST);
+            }
+            __syncwarp();
+        };
+        mbar_wait(kv_full, 0);
+        issue_s_dp(0);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int st = i % ST;
+            mbar_wait(p_full, i & 1);  // P^T / dS^T(i) are in shared memory; S^T / dP^T(i) have been read out
+            if (ST == 2 && i + 1 < n_tiles) issue_s_dp(i + 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qa = smem_u32(sQ(st)), doa = smem_u32(sDO(st));
 #pragma unroll
                 for (int ks = 0; ks < BQ / 16; ++ks) {  // contraction over the queries of this tile
                     const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
@@ -339,9 +378,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     umma_f16(tm_dk, umma_desc_kmajor_sw128(dsta + oa), desc_mn_sw128(qa + ks * 2048, BQ * 128), p.idesc_acc,
                              (i > 0 || ks > 0) ? 1u : 0u);
                 }
-                umma_commit(q_free);
+                umma_commit(&q_free[st]);
+                if (i + 1 == n_tiles) umma_commit(acc_done);
             }
-            umma_commit(acc_done);
+            __syncwarp();
+            if (ST == 1 && i + 1 < n_tiles) issue_s_dp(i + 1);
         }
     } else {
         const int r = warp * 32 + lane;  // key row of this thread
@@ -349,7 +390,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const bool key_ok = k0 + r < p.Nk;
         const long long stat_base = (static_cast<long long>(img) * p.heads + head) * p.Nq;
         for (int i = 0; i < n_tiles; ++i) {
-            if (i > 0) mbar_wait(q_free, (i - 1) & 1);  // previous accumulate MMAs done: P^T / dS^T / stats reusable
+            float* sLse = sStat + (i & 1) * 2 * BQ;  // readers of this buffer (tile i - 2) are behind tile i - 1's bar.sync
+            float* sDel = sLse + BQ;
             if (r < BQ) {
                 const int q = i * BQ + r;
                 sLse[r] = q < p.Nq ? p.lse[stat_base + q] : 0.f;
@@ -365,6 +407,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld_32x32(tm_s + lane_off + c, sr);
                 tmem_ld_32x32(tm_dp + lane_off + c, dr);
                 tmem_ld_wait();
+                // the dV / dK MMAs of the previous tile read P^T / dS^T: done before these are overwritten
+                if (c == 0 && i > 0) mbar_wait(&q_free[(i - 1) % ST], ((i - 1) / ST) & 1);
                 float ls[32], de[32];
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {  // broadcast 16-byte shared loads: every lane reads the same columns
