@@ -53,11 +53,11 @@ def random_weights_(model, seed):
             p.copy_(g)
 
 
-def build_model(device, seed=0):
+def build_model(device, seed=0, config=None):
     from ctrlora_b200 import dropin
     dropin.activate()
     from cldm.model import create_model
-    model = create_model(CONFIG, init_weights=False)
+    model = create_model(config or CONFIG, init_weights=False)
     model = model.to(device).eval()
     random_weights_(model, seed)
     return model
@@ -200,9 +200,11 @@ def run_train(args, rank, local_rank, world, device):
     from ctrlora_b200 import dropin
     dropin.activate()
     from ctrlora_b200.train import FinetuneTrainer
-    model = build_model(device, seed=0)  # identical replicas
+    lora_rank = getattr(args, "lora_rank", 128)
+    cfg = os.path.join(ROOT, "configs", f"ctrlora_finetune_sd15_rank{lora_rank}.yaml")
+    model = build_model(device, seed=0, config=cfg)  # identical replicas
     trainer = FinetuneTrainer(model, lr=1e-5)
-    B = TRAIN_BATCH
+    B = getattr(args, "train_batch", TRAIN_BATCH)
     gen = torch.Generator().manual_seed(200 + rank)
     host = {"x0": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
             "hint": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
@@ -248,7 +250,8 @@ def run_train(args, rank, local_rank, world, device):
     ms_dev, ms_e2e = t.tolist()
     peak_tf, _, peak_src = measured_peaks()
     ips = world * B * args.steps / (ms_dev / 1e3)
-    return {"metric": "train_images_per_sec", "value": ips, "unit": "images/s (512x512, rank 128)", "batch_per_gpu": B,
+    return {"metric": "train_images_per_sec", "value": ips, "unit": f"images/s (512x512, rank {lora_rank})", "batch_per_gpu": B,
+            "lora_rank": lora_rank,
             "ms_per_step": ms_dev / args.steps, "loss": float(loss_host.item()),
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
@@ -265,6 +268,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lora-rank", type=int, default=128, choices=[32, 64, 128, 256, 512],
+                    help="training workload only: BASELINE.json configs[4] rank sweep (default: the rank-128 headline)")
+    ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH, help="training workload: images per GPU per step")
     ap.add_argument("--workload", default="sample+train", choices=["sample", "train", "sample+train"],
                     help="sample: configs[1] DDIM step (the headline line); train: configs[2] finetune step; default: both, "
                          "the training result rides in the line's 'train' key")

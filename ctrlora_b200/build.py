@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src)
                 and os.path.getmtime(obj) >= hdr_m):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CTRLORA_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     rebuilt = bool(procs)
     for src, pr in procs:

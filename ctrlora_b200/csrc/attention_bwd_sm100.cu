@@ -14,7 +14,19 @@
 #include "ctrlora_b200.h"
 #include "gemm_sm100.cuh"
 
+#ifdef CTRLORA_SPIN_WAIT
+#define MBAR_CHAIN_WAIT(bar, par) mbar_wait_spin(bar, par)
+#else
+#define MBAR_CHAIN_WAIT(bar, par) mbar_wait(bar, par)
+#endif
+
 namespace ctrl {
+#ifdef CTRLORA_TIMELINE
+__device__ long long g_tl[4096];
+#define TL(slot) do { if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 4096) g_tl[slot] = clock64(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
 
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
@@ -45,14 +57,12 @@ constexpr int AB_THREADS = 192;  // warps 0-3: row threads, warp 4: TMA, warp 5:
 
 // write 32 fp16 values (packed pairs) of row r, columns [c, c+32) of a K-major SWIZZLE_128B operand tile made of
 // 64-column chunks of `rows` rows each
-__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int rows, int r, int c, const uint32_t* packed) {
-    uint8_t* chunk = tile + (c >> 6) * rows * 128 + r * 128;
+__device__ __forceinline__ void store_row_chunk(uint32_t tile, int rows, int r, int c, const uint32_t* packed) {
+    const uint32_t chunk = tile + (c >> 6) * rows * 128 + r * 128;
     const int u0 = (c & 63) >> 3;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        uint4 val = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = val;
-    }
+    for (int u = 0; u < 4; ++u)
+        sts128(chunk + (((u0 + u) ^ (r & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
 }
 
 // ================================================================================================ D = rowsum(dO * O)
@@ -132,7 +142,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     pdl_wait();
     const uint32_t tm_s = tmem_base, tm_dp = tmem_base + BKV, tm_dq = tmem_base + 2 * BKV;
     const int n_tiles = (p.Nk + BKV - 1) / BKV;
-    const int ksteps_d = (p.d + 15) / 16;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -153,20 +162,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
     } else if (warp == 5) {
         // whole warp in the loop, one elected lane issues (uniform registers for the tcgen05 operands)
-        const uint32_t qa = smem_u32(sQ), doa = smem_u32(sDO), dsa = smem_u32(sDS);
+        // descriptors are built once; per-MMA operands differ by compile-time offsets in the 16-byte address field
+        // (measured with the clock timeline: the first version needed ~650-750 cycles to ISSUE one tile's MMAs, which sat
+        // on the per-tile chain twice: before s_full and before kv_free)
+        constexpr int KS = DPAD / 16;  // k-steps over d (columns >= d are TMA zero fill)
+        const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ)), dDO = umma_desc_kmajor_sw128(smem_u32(sDO)),
+                       dDS = umma_desc_kmajor_sw128(smem_u32(sDS));
+        const uint32_t idesc_s = p.idesc_s, idesc_acc = p.idesc_acc;
         auto issue_s_dp = [&](int j) {  // S = Q K(j)^T, dP = dO V(j)^T
             const int st = j % ST;
             mbar_wait(&kv_full[st], (j / ST) & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t ka = smem_u32(sK(st)), va = smem_u32(sV(st));
-                for (int ks = 0; ks < ksteps_d; ++ks) {
-                    const uint32_t oq = (ks >> 2) * 128 * 128 + (ks & 3) * 32, ok = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
-                    umma_f16(tm_s, umma_desc_kmajor_sw128(qa + oq), umma_desc_kmajor_sw128(ka + ok), p.idesc_s, ks ? 1u : 0u);
+                const uint64_t dK = umma_desc_kmajor_sw128(smem_u32(sK(st))), dV = umma_desc_kmajor_sw128(smem_u32(sV(st)));
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t oq = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, ok = ((ks >> 2) * BKV * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_s, dQ + oq, dK + ok, idesc_s, ks ? 1u : 0u);
                 }
-                for (int ks = 0; ks < ksteps_d; ++ks) {
-                    const uint32_t oq = (ks >> 2) * 128 * 128 + (ks & 3) * 32, ok = (ks >> 2) * BKV * 128 + (ks & 3) * 32;
-                    umma_f16(tm_dp, umma_desc_kmajor_sw128(doa + oq), umma_desc_kmajor_sw128(va + ok), p.idesc_s, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t oq = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, ok = ((ks >> 2) * BKV * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_dp, dDO + oq, dV + ok, idesc_s, ks ? 1u : 0u);
                 }
                 umma_commit(s_full);
             }
@@ -176,16 +193,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         issue_s_dp(0);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % ST;
-            mbar_wait(ds_full, j & 1);  // dS(j) is in shared memory; S / dP(j) have been read out
+            MBAR_CHAIN_WAIT(ds_full, j & 1);  // dS(j) is in shared memory; S / dP(j) have been read out
             if (ST == 2 && j + 1 < n_tiles) issue_s_dp(j + 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t ka = smem_u32(sK(st));
+                const uint64_t dKm = desc_mn_sw128(smem_u32(sK(st)), BKV * 128);
+                const uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {  // contraction over the keys of this tile
-                    const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
-                    umma_f16(tm_dq, umma_desc_kmajor_sw128(dsa + oa), desc_mn_sw128(ka + ks * 2048, BKV * 128), p.idesc_acc,
-                             (j > 0 || ks > 0) ? 1u : 0u);
+                    const uint32_t oa = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_dq, dDS + oa, dKm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
                 }
                 umma_commit(&kv_free[st]);  // K/V stage and the dS tile are free once these MMAs complete
                 if (j + 1 == n_tiles) umma_commit(acc_done);
@@ -201,7 +218,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float lse = row_ok ? p.lse[stat_idx] : 0.f;
         const float dl = row_ok ? p.delta[stat_idx] : 0.f;
         for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(s_full, j & 1);
+            MBAR_CHAIN_WAIT(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = min(BKV, p.Nk - j * BKV);
 #pragma unroll 1
@@ -234,7 +251,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         packed[i >> 1] = pack_half2(ds0, ds1);
                     }
                 }
-                store_row_chunk(sDS, 128, r, c, packed);
+                store_row_chunk(smem_u32(sDS), 128, r, c, packed);
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -322,7 +339,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     pdl_wait();
     const uint32_t tm_s = tmem_base, tm_dp = tmem_base + BQ, tm_dv = tmem_base + 2 * BQ, tm_dk = tm_dv + DPAD;
     const int n_tiles = (p.Nq + BQ - 1) / BQ;
-    const int ksteps_d = (p.d + 15) / 16;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -342,20 +358,25 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
     } else if (warp == 5) {
-        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), pta = smem_u32(sPT), dsta = smem_u32(sDST);
+        constexpr int KS = DPAD / 16;  // k-steps over d (columns >= d are TMA zero fill)
+        const uint64_t dK = umma_desc_kmajor_sw128(smem_u32(sK)), dV = umma_desc_kmajor_sw128(smem_u32(sV)),
+                       dPT = umma_desc_kmajor_sw128(smem_u32(sPT)), dDST = umma_desc_kmajor_sw128(smem_u32(sDST));
+        const uint32_t idesc_s = p.idesc_s, idesc_acc = p.idesc_acc;
         auto issue_s_dp = [&](int i) {  // S^T = K Q(i)^T, dP^T = V dO(i)^T
             const int st = i % ST;
             mbar_wait(&q_full[st], (i / ST) & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t qa = smem_u32(sQ(st)), doa = smem_u32(sDO(st));
-                for (int ks = 0; ks < ksteps_d; ++ks) {
-                    const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
-                    umma_f16(tm_s, umma_desc_kmajor_sw128(ka + ok), umma_desc_kmajor_sw128(qa + oq), p.idesc_s, ks ? 1u : 0u);
+                const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ(st))), dDO = umma_desc_kmajor_sw128(smem_u32(sDO(st)));
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t ok = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, oq = ((ks >> 2) * BQ * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_s, dK + ok, dQ + oq, idesc_s, ks ? 1u : 0u);
                 }
-                for (int ks = 0; ks < ksteps_d; ++ks) {
-                    const uint32_t ok = (ks >> 2) * 128 * 128 + (ks & 3) * 32, oq = (ks >> 2) * BQ * 128 + (ks & 3) * 32;
-                    umma_f16(tm_dp, umma_desc_kmajor_sw128(va + ok), umma_desc_kmajor_sw128(doa + oq), p.idesc_s, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t ok = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, oq = ((ks >> 2) * BQ * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_dp, dV + ok, dDO + oq, idesc_s, ks ? 1u : 0u);
                 }
                 umma_commit(s_full);
             }
@@ -365,23 +386,25 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         issue_s_dp(0);
         for (int i = 0; i < n_tiles; ++i) {
             const int st = i % ST;
-            mbar_wait(p_full, i & 1);  // P^T / dS^T(i) are in shared memory; S^T / dP^T(i) have been read out
+            MBAR_CHAIN_WAIT(p_full, i & 1);  // P^T / dS^T(i) are in shared memory; S^T / dP^T(i) have been read out
+            TL(2048 + i * 4 + 0);
             if (ST == 2 && i + 1 < n_tiles) issue_s_dp(i + 1);
+            TL(2048 + i * 4 + 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t qa = smem_u32(sQ(st)), doa = smem_u32(sDO(st));
+                const uint64_t dQm = desc_mn_sw128(smem_u32(sQ(st)), BQ * 128), dDOm = desc_mn_sw128(smem_u32(sDO(st)), BQ * 128);
+                const uint32_t acc = i > 0 ? 1u : 0u;
 #pragma unroll
                 for (int ks = 0; ks < BQ / 16; ++ks) {  // contraction over the queries of this tile
-                    const uint32_t oa = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
-                    umma_f16(tm_dv, umma_desc_kmajor_sw128(pta + oa), desc_mn_sw128(doa + ks * 2048, BQ * 128), p.idesc_acc,
-                             (i > 0 || ks > 0) ? 1u : 0u);
-                    umma_f16(tm_dk, umma_desc_kmajor_sw128(dsta + oa), desc_mn_sw128(qa + ks * 2048, BQ * 128), p.idesc_acc,
-                             (i > 0 || ks > 0) ? 1u : 0u);
+                    const uint32_t oa = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4;
+                    umma_f16(tm_dv, dPT + oa, dDOm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                    umma_f16(tm_dk, dDST + oa, dQm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
                 }
                 umma_commit(&q_free[st]);
                 if (i + 1 == n_tiles) umma_commit(acc_done);
             }
             __syncwarp();
+            TL(2048 + i * 4 + 2);
             if (ST == 1 && i + 1 < n_tiles) issue_s_dp(i + 1);
         }
     } else {
@@ -389,16 +412,27 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
         const bool key_ok = k0 + r < p.Nk;
         const long long stat_base = (static_cast<long long>(img) * p.heads + head) * p.Nq;
+        // lse / delta of a query tile are fetched one tile ahead (registers) and parked in the other stats buffer at the
+        // end of the iteration: the global-load latency used to sit in front of every tile's bar.sync (ncu: the two
+        // stats stores + the barrier were 15 % of all stall samples)
+        float nl = 0.f, nd = 0.f;
+        if (r < BQ) {
+            sStat[r] = r < p.Nq ? p.lse[stat_base + r] : 0.f;
+            sStat[BQ + r] = r < p.Nq ? p.delta[stat_base + r] : 0.f;
+        }
         for (int i = 0; i < n_tiles; ++i) {
-            float* sLse = sStat + (i & 1) * 2 * BQ;  // readers of this buffer (tile i - 2) are behind tile i - 1's bar.sync
+            float* sLse = sStat + (i & 1) * 2 * BQ;
             float* sDel = sLse + BQ;
-            if (r < BQ) {
-                const int q = i * BQ + r;
-                sLse[r] = q < p.Nq ? p.lse[stat_base + q] : 0.f;
-                sDel[r] = q < p.Nq ? p.delta[stat_base + q] : 0.f;
-            }
+            // stats(i) visible; everyone is done with tile i - 1, so the other buffer may be rewritten at the end of this tile
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(s_full, i & 1);
+            if (r < BQ && i + 1 < n_tiles) {
+                const int q = (i + 1) * BQ + r;
+                nl = q < p.Nq ? p.lse[stat_base + q] : 0.f;
+                nd = q < p.Nq ? p.delta[stat_base + q] : 0.f;
+            }
+            if (warp == 0) TL(i * 8 + 0);
+            MBAR_CHAIN_WAIT(s_full, i & 1);
+            if (warp == 0) TL(i * 8 + 1);
             tc_fence_after();
             const int q_valid = min(BQ, p.Nq - i * BQ);
 #pragma unroll 1
@@ -407,13 +441,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 tmem_ld_32x32(tm_s + lane_off + c, sr);
                 tmem_ld_32x32(tm_dp + lane_off + c, dr);
                 tmem_ld_wait();
+                if (warp == 0) TL(i * 8 + 2 + (c >> 5) * 2);
                 // the dV / dK MMAs of the previous tile read P^T / dS^T: done before these are overwritten
                 if (c == 0 && i > 0) mbar_wait(&q_free[(i - 1) % ST], ((i - 1) / ST) & 1);
+                if (warp == 0) TL(i * 8 + 3 + (c >> 5) * 2);
                 float ls[32], de[32];
 #pragma unroll
                 for (int t = 0; t < 32; t += 4) {  // broadcast 16-byte shared loads: every lane reads the same columns
-                    const float4 a4 = *reinterpret_cast<const float4*>(sLse + c + t);
-                    const float4 b4 = *reinterpret_cast<const float4*>(sDel + c + t);
+                    const float4 a4 = lds128f(smem_u32(sLse + c + t));
+                    const float4 b4 = lds128f(smem_u32(sDel + c + t));
                     ls[t] = a4.x; ls[t + 1] = a4.y; ls[t + 2] = a4.z; ls[t + 3] = a4.w;
                     de[t] = b4.x; de[t + 1] = b4.y; de[t + 2] = b4.z; de[t + 3] = b4.w;
                 }
@@ -441,12 +477,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         dd[t >> 1] = pack_half2(d0, d1);
                     }
                 }
-                store_row_chunk(sPT, 128, r, c, pp);
-                store_row_chunk(sDST, 128, r, c, dd);
+                store_row_chunk(smem_u32(sPT), 128, r, c, pp);
+                store_row_chunk(smem_u32(sDST), 128, r, c, dd);
             }
+            if (warp == 0) TL(i * 8 + 6);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
+            if (warp == 0) TL(i * 8 + 7);
+            if (r < BQ && i + 1 < n_tiles) {
+                float* nb = sStat + ((i + 1) & 1) * 2 * BQ;
+                nb[r] = nl;
+                nb[BQ + r] = nd;
+            }
         }
         mbar_wait(acc_done, 0);
         tc_fence_after();
@@ -582,3 +625,9 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
     }
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
+
+#ifdef CTRLORA_TIMELINE
+extern "C" int ctrlora_debug_timeline(long long* host_out, int n) {
+    return cudaMemcpyFromSymbol(host_out, ctrl::g_tl, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -250,13 +250,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                         packed[i >> 1] = pack_half2(p0, p1);
                     }
                 }
-                uint8_t* chunk = sP + (c >> 6) * 128 * 128 + r * 128;
+                const uint32_t chunk = smem_u32(sP) + (c >> 6) * 128 * 128 + r * 128;
                 const int u0 = (c & 63) >> 3;  // first 16-byte unit of this 32-column group within the 128 B row
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 val = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
-                    *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = val;
-                }
+                for (int u = 0; u < 4; ++u)
+                    sts128(chunk + (((u0 + u) ^ (r & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -322,6 +320,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //   * when d is not a multiple of 16 the zero padding row d of the V^T tile is overwritten with 1.0, so column d of
 //     O IS the row sum (no separate P x ones product).
 //   * the MMA warp issues S(j+1) BEFORE P V(j): the next tile's logits are ready while P V(j) still runs.
+//   * d <= 48: P never goes through shared memory. The row threads write it (fp16 pairs, tcgen05.st) into 64 spare TMEM
+//     columns and P V is issued in the A-from-TMEM form, which costs N/2 = 24 cycles per k-step instead of the
+//     32 + N/4 = 44 of the smem-A form (tools/microbench/mma_issue.cu: the smem A read is the floor for small N).
 constexpr float ATT_TAU = 8.0f;
 
 template <int DPAD>
@@ -365,14 +366,18 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&raw)[32], float s
         }
     }
 }
-__device__ __forceinline__ void store_p_chunk(uint8_t* sP, int r, int c, const uint32_t (&packed)[16]) {
-    uint8_t* chunk = sP + (c >> 6) * 128 * 128 + r * 128;
+__device__ __forceinline__ void store_p_chunk(uint32_t sP, int r, int c, const uint32_t (&packed)[16]) {
+    const uint32_t chunk = sP + (c >> 6) * 128 * 128 + r * 128;
     const int u0 = (c & 63) >> 3;  // first 16-byte unit of this 32-column group within the 128 B row
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) =
-            make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+        sts128(chunk + (((u0 + u) ^ (r & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
 }
+
+template <int DPAD>
+struct StreamCfg {
+    static constexpr bool P_TMEM = DPAD <= 48;  // S 128 | O DPAD | P 64 must fit the 256-column allocation
+};
 
 template <int DPAD>
 __global__ void __launch_bounds__(ATT_THREADS, DPAD <= 48 ? 2 : 1)
@@ -396,6 +401,7 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
     const bool ones_row = p.d < p.d16;  // column d of O doubles as the row sum
+    const bool use_pt = StreamCfg<DPAD>::P_TMEM && ones_row;  // P through TMEM (the l columns are not needed then)
 
     uint8_t* sQ = smem;
     auto sK = [&](int stage) { return smem + L::Q_BYTES + stage * L::STAGE_BYTES; };
@@ -427,6 +433,8 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tmem_s = tmem_base;               // [0, 128)
     const uint32_t tmem_o = tmem_base + BKV;         // [128, 128 + DPAD)
     const uint32_t tmem_l = tmem_o + DPAD;           // [128 + DPAD, +16): P x ones (only without the ones row)
+    constexpr bool PT = StreamCfg<DPAD>::P_TMEM;
+    const uint32_t tmem_p = tmem_o + DPAD;           // PT: [128 + DPAD, +64): P as fp16 pairs (needs the ones row: no l columns)
     const int n_tiles = p.n_kv_tiles;
 
     if (warp == 4) {
@@ -486,8 +494,11 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 for (int ks = 0; ks < BKV / 16; ++ks) {
                     const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
                     const uint32_t off_v = (ks >> 2) * L::V_CHUNK + (ks & 3) * 32;
-                    umma_f16(tmem_o, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
-                             (acc | ks) ? 1u : 0u);
+                    if (PT && use_pt)
+                        umma_f16_ts(tmem_o, tmem_p + 8 * ks, umma_desc_kmajor_sw128(va + off_v), p.idesc_pv, (acc | ks) ? 1u : 0u);
+                    else
+                        umma_f16(tmem_o, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
+                                 (acc | ks) ? 1u : 0u);
                 }
                 if (!ones_row) {
 #pragma unroll
@@ -507,6 +518,11 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int r = warp * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
         const float sl2 = p.scale_log2e;
+        const uint32_t sP_a = smem_u32(sP);
+        auto put_p = [&](int c, const uint32_t (&packed)[16]) {
+            if (PT && use_pt) tmem_st_32x16(tmem_p + lane_off + (c >> 1), packed);
+            else store_p_chunk(sP_a, r, c, packed);
+        };
         float mr = -INFINITY;  // lazy reference maximum, already multiplied by scale * log2(e)
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(s_full, j & 1);
@@ -527,19 +543,19 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 tmem_ld_32x32(tmem_s + lane_off + 64, ra);
                 // P V(j-1) reads the P buffer and accumulates into O: both must be done before P(j) is written
                 mbar_wait(pv_full, (j - 1) & 1);
-                store_p_chunk(sP, r, 0, packed);
+                put_p(0, packed);
                 if (full_tile) softmax_chunk<false>(rb, sl2, neg, 32, kv_valid, packed, tmax);
                 else softmax_chunk<true>(rb, sl2, neg, 32, kv_valid, packed, tmax);
-                store_p_chunk(sP, r, 32, packed);
+                put_p(32, packed);
                 tmem_ld_wait();
                 tmem_ld_32x32(tmem_s + lane_off + 96, rb);
                 if (full_tile) softmax_chunk<false>(ra, sl2, neg, 64, kv_valid, packed, tmax);
                 else softmax_chunk<true>(ra, sl2, neg, 64, kv_valid, packed, tmax);
-                store_p_chunk(sP, r, 64, packed);
+                put_p(64, packed);
                 tmem_ld_wait();
                 if (full_tile) softmax_chunk<false>(rb, sl2, neg, 96, kv_valid, packed, tmax);
                 else softmax_chunk<true>(rb, sl2, neg, 96, kv_valid, packed, tmax);
-                store_p_chunk(sP, r, 96, packed);
+                put_p(96, packed);
                 redo = __any_sync(0xffffffffu, tmax * sl2 > mr + ATT_TAU);
             } else {
                 // first tile: the row maximum is needed before anything else
@@ -582,10 +598,11 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     tmem_ld_32x32(tmem_s + lane_off + c, raw);
                     tmem_ld_wait();
                     softmax_chunk<true>(raw, sl2, neg, c, kv_valid, packed, dummy);
-                    store_p_chunk(sP, r, c, packed);
+                    put_p(c, packed);
                 }
             }
-            fence_proxy_async_smem();
+            if (PT && use_pt) tmem_st_wait();
+            else fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
         }

@@ -396,4 +396,51 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* v)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Spin on mbarrier.test_wait (no hardware suspend): lowest wake-up latency, for waits that sit on a per-tile critical chain.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    long long t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!ok) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000LL) { printf("ctrlora: mbarrier spin timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
+        }
+    } while (!ok);
+}
+// ---------------------------------------------------------------- explicit shared-space 16-byte accesses
+// Pointers derived from the aligned dynamic-smem base are generic to the compiler (LD.E / ST.E through the LSU's global
+// path, "lg throttle" stalls in the row-math loops); these take a 32-bit shared address and emit LDS / STS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand ([128 lanes] x [K/2 32-bit columns], two fp16 per column, written with
+// tcgen05.st by the thread that owns the lane) never touches shared memory: no 4 KiB-per-MMA smem A read (the SS form
+// costs max(N/2, 32 + N/4) cycles per K=16 step, this one N/2 -- tools/microbench/mma_issue.cu).
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 }  // namespace ctrl

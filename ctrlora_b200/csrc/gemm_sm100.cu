@@ -28,13 +28,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, c
     // sb: this tile's bias staged in shared memory (zeros where there is no bias / beyond N): broadcast 16-byte reads
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+        const float4 b4 = lds128f(smem_u32(sb + c + 4 * q));
         v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
     }
     if (GEGLU) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * q);
+            const float4 b4 = lds128f(smem_u32(sb + 256 + c + 4 * q));
             v[4 * q] *= gelu_erf_f(g[4 * q] + b4.x);
             v[4 * q + 1] *= gelu_erf_f(g[4 * q + 1] + b4.y);
             v[4 * q + 2] *= gelu_erf_f(g[4 * q + 2] + b4.z);
@@ -364,8 +364,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     bv = __ldg(p.bias + n0 + e);
                     if (GEGLU) bg = __ldg(p.bias + p.N + n0 + e);
                 }
-                sb[e] = bv;
-                if (GEGLU) sb[256 + e] = bg;
+                sts32f(smem_u32(sb + e), bv);
+                if (GEGLU) sts32f(smem_u32(sb + 256 + e), bg);
             }
             // ---- TMA epilogue: make sure this tile's staging buffer is free (our own bulk stores of `nbuf` tiles ago
             // have finished reading it); with a residual the buffer is handed back to the producer warp instead
@@ -395,10 +395,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // ---- TMEM -> registers -> swizzled staging (in place over the residual tile) -> TMA store per warp
                 if (p.epi_res) mbar_wait(&rfull[sbuf], sphase);
                 uint8_t* stg = smem + p.epi_off + sbuf * p.epi_buf_bytes;
+                const uint32_t sb_a = smem_u32(sb);
                 const int nblk = p.epi_nfull + p.epi_tail;
                 for (int b = half; b < nblk; b += 2) {  // the two warps of a lane group take alternate 64-column blocks
                     const bool tail = b == p.epi_nfull;
-                    uint8_t* rowp = stg + b * 16384 + (tail ? r * 64 : r * 128);
+                    const uint32_t rowp = smem_u32(stg) + b * 16384 + (tail ? r * 64 : r * 128);
                     const int sw = tail ? ((r >> 1) & 3) : (r & 7);
                     for (int cc = 0; cc < (tail ? 1 : 2); ++cc) {
                         const int c = 64 * b + 32 * cc;
@@ -411,8 +412,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tmem_ld_wait();
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
-                                const float4 g4 = *reinterpret_cast<const float4*>(sb + 256 + c + 4 * q);
+                                const float4 b4 = lds128f(sb_a + (c + 4 * q) * 4);
+                                const float4 g4 = lds128f(sb_a + (256 + c + 4 * q) * 4);
                                 v[4 * q] = (__uint_as_float(raw[4 * q]) + b4.x) * gelu_erf_f(__uint_as_float(graw[4 * q]) + g4.x);
                                 v[4 * q + 1] = (__uint_as_float(raw[4 * q + 1]) + b4.y) * gelu_erf_f(__uint_as_float(graw[4 * q + 1]) + g4.y);
                                 v[4 * q + 2] = (__uint_as_float(raw[4 * q + 2]) + b4.z) * gelu_erf_f(__uint_as_float(graw[4 * q + 2]) + g4.z);
@@ -422,7 +423,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tmem_ld_wait();
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * q);
+                                const float4 b4 = lds128f(sb_a + (c + 4 * q) * 4);
                                 v[4 * q] = __uint_as_float(raw[4 * q]) + b4.x;
                                 v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b4.y;
                                 v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b4.z;
@@ -441,9 +442,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4* sp = reinterpret_cast<uint4*>(rowp + (((4 * cc + q) ^ sw) << 4));
+                            const uint32_t sp = rowp + (((4 * cc + q) ^ sw) << 4);
                             if (p.epi_res) {
-                                const uint4 x = *sp;
+                                const uint4 x = lds128(sp);
                                 const __half2* h = reinterpret_cast<const __half2*>(&x);
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -452,12 +453,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     v[q * 8 + e * 2 + 1] += f.y;
                                 }
                             }
-                            uint4 u;
-                            u.x = pack_h2(v[q * 8 + 0], v[q * 8 + 1]);
-                            u.y = pack_h2(v[q * 8 + 2], v[q * 8 + 3]);
-                            u.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
-                            u.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
-                            *sp = u;
+                            sts128(sp, pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
+                                   pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
                         }
                     }
                 }

@@ -84,6 +84,19 @@ def attn_cases():
               f"{B * H * nq * nk / ms / 1e6:7.1f} Gexp/s")
 
 
+def attn_bwd_cases():
+    H = 8
+    for B, nq, nk, d in [(16, 4096, 4096, 40), (16, 1024, 1024, 80), (16, 4096, 77, 40)]:
+        q, k, v = rnd(B * nq, H * d), rnd(B * nk, H * d), rnd(B * nk, H * d)
+        o, do = rnd(B * nq, H * d), rnd(B * nq, H * d)
+        lse = torch.randn(B, H, nq, device="cuda") + 8.0
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ms = timeit(lambda: ops.attention_bwd(q, k, v, o, do, lse, B, H, nq, nk, d, dq=dq, dk=dk, dv=dv))
+        fl = 10.0 * B * H * nq * nk * d
+        print(f"attn_bwd B={B} nq={nq} nk={nk} d={d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  "
+              f"{2 * B * H * nq * nk / ms / 1e6:7.1f} Gexp/s")
+
+
 def norm_cases():
     B = 8
     for h, c in [(64, 320), (32, 640), (16, 1280), (64, 640), (8, 1280)]:
@@ -104,5 +117,7 @@ if __name__ == "__main__":
         gemm_cases()
     if "attn" in which:
         attn_cases()
+    if "attnbwd" in which:
+        attn_bwd_cases()
     if "norm" in which:
         norm_cases()
