@@ -107,6 +107,13 @@ struct DqSmem {
     static constexpr int TOTAL = DATA + 1024 + 128;
 };
 
+// TS: every A operand of the dQ kernel lives in TMEM (d <= 48, 64-key tiles: S 64 | dP 64 | dQ 48 | dS 32 | Q 24 | dO 24
+// = 256 columns). Q and dO rows are copied once from their TMA tiles by the thread that owns the row; dS is written
+// straight from the row math. An A-from-TMEM MMA costs N/2 cycles per k-step instead of 32 + N/4 (the smem A read,
+// tools/microbench/mma_issue.cu): 288 instead of 464 tensor cycles per 128x64 tile.
+template <int DPAD, int BKV>
+struct DqTs { static constexpr bool ON = (DPAD == 48 && BKV == 64); };
+
 template <int DPAD, int BKV>
 __global__ void __launch_bounds__(AB_THREADS, (2 * BKV + DPAD <= 256) ? 2 : 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
@@ -122,8 +129,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto sV = [&](int st) { return smem + L::OFF_V + st * L::STAGE_BYTES; };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA);
     uint64_t *q_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_free = bars + 3 /*[2]*/, *s_full = bars + 5, *ds_full = bars + 6,
-             *acc_done = bars + 7;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+             *acc_done = bars + 7, *a_ready = bars + 8;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+    constexpr bool TS = DqTs<DPAD, BKV>::ON;
     constexpr uint32_t TMEM_COLS = (2 * BKV + DPAD <= 256) ? 256 : 512;  // 256 columns: two CTAs share an SM's TMEM
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
@@ -131,7 +139,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1); mbar_init(s_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_free[i], 1); }
-        mbar_init(ds_full, 128); mbar_init(acc_done, 1);
+        mbar_init(ds_full, 128); mbar_init(acc_done, 1); mbar_init(a_ready, 128);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -141,6 +149,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();
     const uint32_t tm_s = tmem_base, tm_dp = tmem_base + BKV, tm_dq = tmem_base + 2 * BKV;
+    const uint32_t tm_ds16 = tm_dq + DPAD, tm_q16 = tm_ds16 + BKV / 2, tm_do16 = tm_q16 + DPAD / 2;  // TS only
     const int n_tiles = (p.Nk + BKV - 1) / BKV;
 
     if (warp == 4) {
@@ -178,18 +187,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     const uint32_t oq = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, ok = ((ks >> 2) * BKV * 128 + (ks & 3) * 32) >> 4;
-                    umma_f16(tm_s, dQ + oq, dK + ok, idesc_s, ks ? 1u : 0u);
+                    if (TS) umma_f16_ts(tm_s, tm_q16 + 8 * ks, dK + ok, idesc_s, ks ? 1u : 0u);
+                    else umma_f16(tm_s, dQ + oq, dK + ok, idesc_s, ks ? 1u : 0u);
                 }
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     const uint32_t oq = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4, ok = ((ks >> 2) * BKV * 128 + (ks & 3) * 32) >> 4;
-                    umma_f16(tm_dp, dDO + oq, dV + ok, idesc_s, ks ? 1u : 0u);
+                    if (TS) umma_f16_ts(tm_dp, tm_do16 + 8 * ks, dV + ok, idesc_s, ks ? 1u : 0u);
+                    else umma_f16(tm_dp, dDO + oq, dV + ok, idesc_s, ks ? 1u : 0u);
                 }
                 umma_commit(s_full);
             }
             __syncwarp();
         };
-        mbar_wait(q_full, 0);
+        if (TS) mbar_wait(a_ready, 0);  // the row threads have copied their Q / dO rows into TMEM
+        else mbar_wait(q_full, 0);
         issue_s_dp(0);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j % ST;
@@ -202,7 +214,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int ks = 0; ks < BKV / 16; ++ks) {  // contraction over the keys of this tile
                     const uint32_t oa = ((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4;
-                    umma_f16(tm_dq, dDS + oa, dKm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                    if (TS) umma_f16_ts(tm_dq, tm_ds16 + 8 * ks, dKm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                    else umma_f16(tm_dq, dDS + oa, dKm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
                 }
                 umma_commit(&kv_free[st]);  // K/V stage and the dS tile are free once these MMAs complete
                 if (j + 1 == n_tiles) umma_commit(acc_done);
@@ -217,6 +230,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const long long stat_idx = (static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r;
         const float lse = row_ok ? p.lse[stat_idx] : 0.f;
         const float dl = row_ok ? p.delta[stat_idx] : 0.f;
+        if (TS) {
+            // row r of the Q / dO TMA tiles (SWIZZLE_128B: 16-byte unit u sits at u ^ (r & 7); columns >= d are zero fill)
+            mbar_wait(q_full, 0);
+            const uint32_t rq = smem_u32(sQ) + r * 128, rdo = smem_u32(sDO) + r * 128;
+            uint32_t w[24];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const uint4 x = lds128(rq + ((u ^ (r & 7)) << 4));
+                w[4 * u] = x.x; w[4 * u + 1] = x.y; w[4 * u + 2] = x.z; w[4 * u + 3] = x.w;
+            }
+            tmem_st_32x16(tm_q16 + lane_off, w);
+            tmem_st_32x8(tm_q16 + lane_off + 16, w + 16);
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const uint4 x = lds128(rdo + ((u ^ (r & 7)) << 4));
+                w[4 * u] = x.x; w[4 * u + 1] = x.y; w[4 * u + 2] = x.z; w[4 * u + 3] = x.w;
+            }
+            tmem_st_32x16(tm_do16 + lane_off, w);
+            tmem_st_32x8(tm_do16 + lane_off + 16, w + 16);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(a_ready);
+        }
         for (int j = 0; j < n_tiles; ++j) {
             MBAR_CHAIN_WAIT(s_full, j & 1);
             tc_fence_after();
@@ -251,9 +287,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         packed[i >> 1] = pack_half2(ds0, ds1);
                     }
                 }
-                store_row_chunk(smem_u32(sDS), 128, r, c, packed);
+                if (TS) tmem_st_32x16(tm_ds16 + lane_off + (c >> 1), packed);
+                else store_row_chunk(smem_u32(sDS), 128, r, c, packed);
             }
-            fence_proxy_async_smem();
+            if (TS) tmem_st_wait();
+            else fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_full);
         }

@@ -62,8 +62,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, c
     }
     if (p.residual && p.residual_f32) {
         const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
-        for (int j = 0; j < 32; ++j)
-            if (c + j < bn_out && nbase + j < p.N) v[j] += rp[j];
+        if (full_chunk && (p.ldr & 3) == 0) {  // LoRA folds: W (fp32 master) + s * up . down
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp) + q);
+                v[4 * q] += r4.x; v[4 * q + 1] += r4.y; v[4 * q + 2] += r4.z; v[4 * q + 3] += r4.w;
+            }
+        } else {
+            for (int j = 0; j < 32; ++j)
+                if (c + j < bn_out && nbase + j < p.N) v[j] += rp[j];
+        }
     } else if (p.residual) {
         const __half* rp = p.residual + m * p.ldr + nbase;
         if (full_chunk && (p.ldr & 7) == 0) {
@@ -133,9 +141,7 @@ template <bool GEGLU, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCt,
-                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmRt,
-                    const __grid_constant__ GemmKParams p) {
+                    const __grid_constant__ GemmEpiMaps em, const __grid_constant__ GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_SMEM_DATA);
@@ -162,9 +168,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (p.epi_tma) {
-            tma_prefetch_desc(&tmC);
-            tma_prefetch_desc(&tmCt);
-            if (p.epi_res) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmRt); }
+            tma_prefetch_desc(&em.out[0][0]);
+            tma_prefetch_desc(&em.out[0][1]);
+            if (p.epi_res) { tma_prefetch_desc(&em.res[0]); tma_prefetch_desc(&em.res[1]); }
         }
         if (p.kchunks2 > 0) {
             tma_prefetch_desc(&tmA2);
@@ -281,9 +287,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t dst = smem0 + p.epi_off + rbuf * p.epi_buf_bytes;
                         mbar_expect_tx_a(rb, GEMM_BM * bn_out * 2);
                         for (int b = 0; b < p.epi_nfull; ++b)
-                            tma_load_4d_a<false>(dst + b * 16384, &tmR, rb, n0 + 64 * b, w0 + pad, h0 + pad, b0);
+                            tma_load_4d_a<false>(dst + b * 16384, &em.res[0], rb, n0 + 64 * b, w0 + pad, h0 + pad, b0);
                         if (p.epi_tail)
-                            tma_load_4d_a<false>(dst + p.epi_nfull * 16384, &tmRt, rb, n0 + 64 * p.epi_nfull, w0 + pad, h0 + pad, b0);
+                            tma_load_4d_a<false>(dst + p.epi_nfull * 16384, &em.res[1], rb, n0 + 64 * p.epi_nfull, w0 + pad, h0 + pad, b0);
                     }
                     __syncwarp();
                     if (++rbuf == p.epi_nbuf) { rbuf = 0; rphase ^= 1; }
@@ -397,6 +403,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint8_t* stg = smem + p.epi_off + sbuf * p.epi_buf_bytes;
                 const uint32_t sb_a = smem_u32(sb);
                 const int nblk = p.epi_nfull + p.epi_tail;
+                // output segment of this tile (q | k | v projections share one GEMM); a transposed segment (V^T for the
+                // attention kernels) is stored straight from registers -- thread = token makes THAT store the coalesced
+                // one -- and only its natural-layout duplicate (training) goes through the staging buffer
+                const int seg = p.seg_width > 0 ? n0 / p.seg_width : 0;
+                const int nloc0 = n0 - seg * p.seg_width;
+                const bool tr = p.transposed[seg] != 0;
+                const bool stage_it = !tr || p.dup_out != nullptr;
+                __half* ot = nullptr;
+                if (tr) ot = reinterpret_cast<__half*>(p.out[seg]) + (static_cast<long long>(img) * p.seg_width + nloc0) * p.tok_pad + tok;
                 for (int b = half; b < nblk; b += 2) {  // the two warps of a lane group take alternate 64-column blocks
                     const bool tail = b == p.epi_nfull;
                     const uint32_t rowp = smem_u32(stg) + b * 16384 + (tail ? r * 64 : r * 128);
@@ -440,6 +455,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
                         }
+                        if (tr && row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + c + j < p.N) ot[static_cast<long long>(c + j) * p.tok_pad] = __float2half_rn(v[j]);
+                        }
+                        if (stage_it)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t sp = rowp + (((4 * cc + q) ^ sw) << 4);
@@ -466,9 +487,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int r0 = lane_grp * 32;  // this warp's 32 rows are a rectangular sub-box of the tile's pixel box
                     const int cw = tw * p.bw + r0 % p.bw, ch = th * p.bh + (r0 / p.bw) % p.bh, cb = tb * p.nb + r0 / (p.bw * p.bh);
                     const uint32_t s0 = smem_u32(stg);
-                    for (int b = half; b < nblk; b += 2) {
-                        if (b == p.epi_nfull) tma_store_4d(&tmCt, s0 + b * 16384 + lane_grp * 2048, n0 + 64 * b, cw, ch, cb);
-                        else tma_store_4d(&tmC, s0 + b * 16384 + lane_grp * 4096, n0 + 64 * b, cw, ch, cb);
+                    if (stage_it) {
+                        const CUtensorMap* m64 = tr ? &em.dup[0] : &em.out[seg][0];
+                        const CUtensorMap* m32 = tr ? &em.dup[1] : &em.out[seg][1];
+                        for (int b = half; b < nblk; b += 2) {
+                            if (b == p.epi_nfull) tma_store_4d(m32, s0 + b * 16384 + lane_grp * 2048, nloc0 + 64 * b, cw, ch, cb);
+                            else tma_store_4d(m64, s0 + b * 16384 + lane_grp * 4096, nloc0 + 64 * b, cw, ch, cb);
+                        }
                     }
                     bulk_commit_group();
                 }
@@ -674,9 +699,17 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         epi_env = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;  // 0: direct only, 1: per-shape policy, 2: wherever legal
     }
     // TMA-staged epilogue (see below): legal for plain fp16 row-major outputs; wanted where the k loop is short
-    const bool epi_legal = !a->out_f32 && a->split_k <= 1 && a->seg_width == 0 && !a->transposed[0] && !a->dup_out &&
-                           a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out[0]) & 15) == 0 &&
-                           (!a->residual || (!a->residual_f32 && a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0));
+    bool epi_legal = !a->out_f32 && a->split_k <= 1 && a->ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out[0]) & 15) == 0 &&
+                     (!a->residual || (!a->residual_f32 && a->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0));
+    if (a->seg_width > 0) {  // q | k | v segments: plain segments need aligned bases, a transposed one may carry a duplicate
+        const int nseg = (a->n + a->seg_width - 1) / a->seg_width;
+        if (a->residual || nseg > 3 || a->seg_width % 8 != 0) epi_legal = false;
+        for (int i = 0; i < nseg && i < 3; ++i)
+            if (!a->transposed[i] && (!a->out[i] || (reinterpret_cast<uintptr_t>(a->out[i]) & 15) != 0)) epi_legal = false;
+        if (a->dup_out && ((reinterpret_cast<uintptr_t>(a->dup_out) & 15) != 0 || a->dup_ld % 8 != 0)) epi_legal = false;
+    } else if (a->transposed[0] || a->dup_out) {
+        epi_legal = false;
+    }
     const bool epi_wanted = epi_legal && (epi_env == 2 || (epi_env == 1 && k_iters <= 32));
     int bn_out = a->block_n, splits = a->split_k > 0 ? a->split_k : 1;
     if (bn_out <= 0) {
@@ -799,27 +832,40 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         tmA2 = tmA;
         tmB2 = tmB;
     }
-    CUtensorMap tmC = tmA, tmCt = tmA, tmR = tmA, tmRt = tmA;
+    GemmEpiMaps em;
+    for (int i = 0; i < 3; ++i) { em.out[i][0] = tmA; em.out[i][1] = tmA; }
+    em.dup[0] = em.dup[1] = em.res[0] = em.res[1] = tmA;
     if (p.epi_tma) {
         // output: per-warp stores of a 32-row sub-box of the tile's (bw, bh, nb) pixel box; residual: whole-tile loads
         const int sw = p.bw < 32 ? p.bw : 32;
         const int sh = p.bh < 32 / sw ? p.bh : 32 / sw;
         const int sb = 32 / (sw * sh);
-        uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
-        uint64_t str[3] = {(uint64_t)a->ldc * 2, (uint64_t)a->ldc * 2 * p.W, (uint64_t)a->ldc * 2 * p.W * p.H};
-        uint32_t box[4] = {64, (uint32_t)sw, (uint32_t)sh, (uint32_t)sb};
-        int rc = make_tmap_f16_sw(&tmC, a->out[0], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        box[0] = 32;
-        rc = make_tmap_f16_sw(&tmCt, a->out[0], 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
-        if (rc) return rc;
-        if (p.epi_res) {
-            uint64_t rstr[3] = {(uint64_t)a->ldr * 2, (uint64_t)a->ldr * 2 * p.W, (uint64_t)a->ldr * 2 * p.W * p.H};
-            uint32_t rbox[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.nb};
-            rc = make_tmap_f16_sw(&tmR, a->residual, 4, dims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_128B);
+        auto pair_of = [&](CUtensorMap* dst, const void* base, long long ld, int cols, int bw_, int bh_, int nb_) -> int {
+            uint64_t dims[4] = {(uint64_t)cols, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.Bn};
+            uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * p.W, (uint64_t)ld * 2 * p.W * p.H};
+            uint32_t box[4] = {64, (uint32_t)bw_, (uint32_t)bh_, (uint32_t)nb_};
+            int rc = make_tmap_f16_sw(&dst[0], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc) return rc;
-            rbox[0] = 32;
-            rc = make_tmap_f16_sw(&tmRt, a->residual, 4, dims, rstr, rbox, CU_TENSOR_MAP_SWIZZLE_64B);
+            box[0] = 32;
+            return make_tmap_f16_sw(&dst[1], base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        };
+        if (a->seg_width > 0) {
+            const int nseg = (p.N + a->seg_width - 1) / a->seg_width;
+            for (int i = 0; i < nseg; ++i) {
+                if (a->transposed[i]) continue;
+                int rc = pair_of(em.out[i], a->out[i], a->ldc, a->seg_width, sw, sh, sb);
+                if (rc) return rc;
+            }
+            if (a->dup_out) {
+                int rc = pair_of(em.dup, a->dup_out, a->dup_ld, a->seg_width, sw, sh, sb);
+                if (rc) return rc;
+            }
+        } else {
+            int rc = pair_of(em.out[0], a->out[0], a->ldc, p.N, sw, sh, sb);
+            if (rc) return rc;
+        }
+        if (p.epi_res) {
+            int rc = pair_of(em.res, a->residual, a->ldr, p.N, p.bw, p.bh, p.nb);
             if (rc) return rc;
         }
     }
@@ -837,15 +883,15 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
         int clusters = g_num_sms / 2;
         if (units < clusters) clusters = units;
         const dim3 grid2(2 * clusters), block(GEMM_THREADS);
-        lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p)
-                      : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p);
+        lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, em, p)
+                      : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, em, p);
     } else {
         const int total = m_tiles * p.n_tiles * p.splits;
         const int grid = total < g_num_sms ? total : g_num_sms;
         lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                   stream, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p)
+                                   stream, tmA, tmB, tmA2, tmB2, em, p)
                       : launch_pdl(gemm_tcgen05_kernel<false, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
-                                   stream, tmA, tmB, tmA2, tmB2, tmC, tmCt, tmR, tmRt, p);
+                                   stream, tmA, tmB, tmA2, tmB2, em, p);
     }
     if (lrc != cudaSuccess) return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;

@@ -13,6 +13,15 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0: TMA producer,
 constexpr int GEMM_SMEM_DATA = 216 * 1024;            // ring buffer budget
 constexpr int GEMM_SMEM_BYTES = GEMM_SMEM_DATA + 1024 /*align slack*/ + 512 /*barriers*/ + 4096 /*bias staging*/;
 
+// Tensor maps of the TMA-staged epilogue: per output segment a 64-column SWIZZLE_128B map and a 32-column SWIZZLE_64B
+// map (32-row sub-box stores), the same pair for the natural-layout duplicate of a transposed segment, and the
+// whole-tile pair of the fp16 residual.
+struct GemmEpiMaps {
+    CUtensorMap out[3][2];
+    CUtensorMap dup[2];
+    CUtensorMap res[2];
+};
+
 struct GemmKParams {
     // tile geometry over the (B, H, W) pixel grid; a plain [M, K] matrix is B=1, H=1, W=M
     int W, H, Bn;

@@ -28,6 +28,18 @@ if __name__ == "__main__":
     for _ in range(2):
         trainer.step(x0, hint, ctx, t, noise)
     torch.cuda.synchronize()
+    if len(sys.argv) > 2:  # python tools/profile_train.py 16 gpurun_out/gemm_shapes_train.json : per-GEMM CUDA-event timings
+        import json
+        from ctrlora_b200 import ops
+        ops._GEMM_PROFILE, ops._GEMM_SHAPES = [], []
+        trainer.step(x0, hint, ctx, t, noise)
+        torch.cuda.synchronize()
+        recs = [dict(shape, ms=r[1].elapsed_time(r[2]), gflop=r[0] / 1e9) for shape, r in zip(ops._GEMM_SHAPES, ops._GEMM_PROFILE)]
+        ops._GEMM_PROFILE = ops._GEMM_SHAPES = None
+        json.dump(recs, open(sys.argv[2], "w"), indent=0)
+        tot = sum(r["ms"] for r in recs)
+        print(f"{len(recs)} GEMM launches, {tot:.2f} ms, {sum(r['gflop'] for r in recs) / tot:.1f} TFLOP/s average")
+        sys.exit(0)
     torch.cuda.profiler.start()
     trainer.step(x0, hint, ctx, t, noise)
     torch.cuda.synchronize()
