@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "ctrlora_b200.h"
 #include "gemm_sm100.cuh"
+#include <stdlib.h>
 
 #ifdef CTRLORA_SPIN_WAIT
 #define MBAR_CHAIN_WAIT(bar, par) mbar_wait_spin(bar, par)
@@ -564,6 +565,266 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ================================================================================================ dK, dV, all-TMEM
+// d <= 48 (the 64x64 level: almost all of the backward attention time). One CTA per SM with the whole 512-column TMEM:
+//   S^T / dP^T double-buffered (2 x 128 columns): the products of query tile i+1 (and i+2) are computed while the row
+//     threads work on tile i -- the row math never waits for the tensor pipe;
+//   every A operand in TMEM: K and V rows copied once (thread = key row), P^T and dS^T written by the row math
+//     (tcgen05.st) -- an A-from-TMEM MMA costs N/2 cycles per k-step instead of 32 + N/4 (tools/microbench/mma_issue.cu):
+//     384 instead of 640 tensor cycles per 128 x 64 tile, and no shared-memory round trip for P^T / dS^T.
+//   columns: S^T0 64 | dP^T0 64 | S^T1 64 | dP^T1 64 | dV 48 | dK 48 | P^T 32 | dS^T 32 | K 24 | V 24 = 464.
+struct DkvTsSmem {
+    static constexpr int BQ = 64, ST = 4;
+    static constexpr int KV_BYTES = 128 * 128;          // K and V: [128 keys][128 B] (one 64-column chunk, d <= 48)
+    static constexpr int Q_BYTES = BQ * 128;            // Q and dO tile: [64 queries][128 B]
+    static constexpr int STAGE_BYTES = 2 * Q_BYTES;
+    static constexpr int OFF_V = KV_BYTES, OFF_Q = 2 * KV_BYTES, OFF_STAT = OFF_Q + ST * STAGE_BYTES;
+    static constexpr int DATA = OFF_STAT + 2 * 2 * BQ * 4;
+    static constexpr int BAR = (DATA + 127) / 128 * 128;
+    static constexpr int TOTAL = BAR + 1024 + 256;
+};
+
+constexpr int DKV_TS_THREADS = 320;  // warps 0-7: row math (lane group = warp & 3, 32-query half = warp >> 2), 8: TMA, 9: MMA
+
+__global__ void __launch_bounds__(DKV_TS_THREADS, 1)
+attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ AttnBwdParams p) {
+    using L = DkvTsSmem;
+    constexpr int BQ = L::BQ, ST = L::ST, DPAD = 48, KS = DPAD / 16;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sK = smem, *sV = smem + L::OFF_V;
+    auto sQ = [&](int st) { return smem + L::OFF_Q + st * L::STAGE_BYTES; };
+    auto sDO = [&](int st) { return smem + L::OFF_Q + st * L::STAGE_BYTES + L::Q_BYTES; };
+    float* sStat = reinterpret_cast<float*>(smem + L::OFF_STAT);  // [2 buffers][lse BQ | delta BQ]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+    uint64_t *kv_full = bars, *q_full = bars + 1 /*[4]*/, *q_free = bars + 5 /*[4]*/, *s_full = bars + 9 /*[2]*/, *p_full = bars + 11,
+             *acc_done = bars + 12, *a_ready = bars + 13;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    if (warp == 9 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < ST; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_free[i], 1); }
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(p_full, 256); mbar_init(acc_done, 1); mbar_init(a_ready, 256);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tm_sdp = tmem_base;                 // buffer b: S^T at + 128 b, dP^T at + 128 b + 64
+    const uint32_t tm_dv = tmem_base + 256, tm_dk = tm_dv + DPAD;
+    const uint32_t tm_pt = tm_dk + DPAD, tm_dst = tm_pt + BQ / 2, tm_k16 = tm_dst + BQ / 2, tm_v16 = tm_k16 + DPAD / 2;
+    const int n_tiles = (p.Nq + BQ - 1) / BQ;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * 128 * 128);
+            tma_load_4d(sK, &tmK, kv_full, 0, head, k0, img);
+            tma_load_4d(sV, &tmV, kv_full, 0, head, k0, img);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int st = i % ST;
+                if (i >= ST) mbar_wait(&q_free[st], ((i / ST) - 1) & 1);
+                mbar_expect_tx(&q_full[st], 2 * BQ * 128);
+                tma_load_4d(sQ(st), &tmQ, &q_full[st], 0, head, i * BQ, img);
+                tma_load_4d(sDO(st), &tmDO, &q_full[st], 0, head, i * BQ, img);
+            }
+        }
+    } else if (warp == 9) {
+        const uint32_t idesc_s = p.idesc_s, idesc_acc = p.idesc_acc;
+        auto issue_s_dp = [&](int i) {  // S^T = K Q(i)^T, dP^T = V dO(i)^T into buffer i & 1
+            const int st = i % ST;
+            mbar_wait(&q_full[st], (i / ST) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dQ = umma_desc_kmajor_sw128(smem_u32(sQ(st))), dDO = umma_desc_kmajor_sw128(smem_u32(sDO(st)));
+                const uint32_t ts = tm_sdp + 128 * (i & 1);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) umma_f16_ts(ts, tm_k16 + 8 * ks, dQ + 2 * ks, idesc_s, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) umma_f16_ts(ts + 64, tm_v16 + 8 * ks, dDO + 2 * ks, idesc_s, ks ? 1u : 0u);
+                umma_commit(&s_full[i & 1]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(a_ready, 0);  // K / V rows are in TMEM
+        issue_s_dp(0);
+        if (n_tiles > 1) issue_s_dp(1);
+        for (int i = 0; i < n_tiles; ++i) {
+            const int st = i % ST;
+            mbar_wait(p_full, i & 1);  // P^T / dS^T(i) are in TMEM; buffer i & 1 of S^T / dP^T has been read out
+            TL(2048 + i * 4 + 0);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dQm = desc_mn_sw128(smem_u32(sQ(st)), BQ * 128), dDOm = desc_mn_sw128(smem_u32(sDO(st)), BQ * 128);
+                const uint32_t acc = i > 0 ? 1u : 0u;
+#pragma unroll
+                for (int ks = 0; ks < BQ / 16; ++ks) {  // contraction over the queries of this tile
+                    umma_f16_ts(tm_dv, tm_pt + 8 * ks, dDOm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                    umma_f16_ts(tm_dk, tm_dst + 8 * ks, dQm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                }
+                umma_commit(&q_free[st]);  // Q / dO stage and the P^T / dS^T columns are free once these complete
+                if (i + 1 == n_tiles) umma_commit(acc_done);
+            }
+            __syncwarp();
+            TL(2048 + i * 4 + 1);
+            if (i + 2 < n_tiles) issue_s_dp(i + 2);
+            TL(2048 + i * 4 + 2);
+        }
+    } else {
+        // two warps per TMEM lane group: each takes one 32-query half of every tile (nothing couples the columns in
+        // the backward), so every scheduler has two row-math warps to overlap TMEM / MUFU latency
+        const int lg = warp & 3, part = warp >> 2;
+        const int r = lg * 32 + lane;  // key row of this thread
+        const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        const bool key_ok = k0 + r < p.Nk;
+        const long long stat_base = (static_cast<long long>(img) * p.heads + head) * p.Nq;
+        {
+            // this key's K and V rows -> TMEM (SWIZZLE_128B tile: 16-byte unit u sits at u ^ (r & 7); columns >= d are zero)
+            mbar_wait(kv_full, 0);
+            const uint32_t src = smem_u32(part == 0 ? sK : sV) + r * 128;  // part 0 copies K, part 1 copies V
+            const uint32_t dst = (part == 0 ? tm_k16 : tm_v16) + lane_off;
+            uint32_t w[24];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const uint4 x = lds128(src + ((u ^ (r & 7)) << 4));
+                w[4 * u] = x.x; w[4 * u + 1] = x.y; w[4 * u + 2] = x.z; w[4 * u + 3] = x.w;
+            }
+            tmem_st_32x16(dst, w);
+            tmem_st_32x8(dst + 16, w + 16);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(a_ready);
+        }
+        float nl = 0.f, nd = 0.f;
+        if (part == 0 && r < BQ) {
+            sStat[r] = r < p.Nq ? p.lse[stat_base + r] : 0.f;
+            sStat[BQ + r] = r < p.Nq ? p.delta[stat_base + r] : 0.f;
+        }
+        for (int i = 0; i < n_tiles; ++i) {
+            float* sLse = sStat + (i & 1) * 2 * BQ;
+            float* sDel = sLse + BQ;
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // stats(i) visible; the other buffer is free
+            if (part == 0 && r < BQ && i + 1 < n_tiles) {
+                const int q = (i + 1) * BQ + r;
+                nl = q < p.Nq ? p.lse[stat_base + q] : 0.f;
+                nd = q < p.Nq ? p.delta[stat_base + q] : 0.f;
+            }
+            if (warp == 0) TL(i * 8 + 0);
+            mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+            if (warp == 0) TL(i * 8 + 1);
+            tc_fence_after();
+            const int q_valid = min(BQ, p.Nq - i * BQ);
+            const uint32_t ts = tm_sdp + 128 * (i & 1) + lane_off;
+            const bool full = key_ok && q_valid == BQ;
+            {
+                const int c = 32 * part;
+                uint32_t sr[32], dr[32], pp[16], dd[16];
+                tmem_ld_32x32(ts + c, sr);
+                tmem_ld_32x32(ts + 64 + c, dr);
+                tmem_ld_wait();
+                if (warp == 0) TL(i * 8 + 2 + (c >> 5) * 2);
+                float ls[32], de[32];
+#pragma unroll
+                for (int t = 0; t < 32; t += 4) {  // broadcast 16-byte shared loads: every lane reads the same columns
+                    const float4 a4 = lds128f(smem_u32(sLse + c + t));
+                    const float4 b4 = lds128f(smem_u32(sDel + c + t));
+                    ls[t] = a4.x; ls[t + 1] = a4.y; ls[t + 2] = a4.z; ls[t + 3] = a4.w;
+                    de[t] = b4.x; de[t + 1] = b4.y; de[t + 2] = b4.z; de[t + 3] = b4.w;
+                }
+                if (full) {  // straight-line: the masked form below compiles to a branch per element
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -ls[t]));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -ls[t + 1]));
+                        pp[t >> 1] = pack_half2(p0, p1);
+                        dd[t >> 1] = pack_half2(p0 * (__uint_as_float(dr[t]) - de[t]), p1 * (__uint_as_float(dr[t + 1]) - de[t + 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                        if (key_ok && c + t < q_valid) {
+                            p0 = fast_exp2(fmaf(__uint_as_float(sr[t]), p.scale_log2e, -ls[t]));
+                            d0 = p0 * (__uint_as_float(dr[t]) - de[t]);
+                        }
+                        if (key_ok && c + t + 1 < q_valid) {
+                            p1 = fast_exp2(fmaf(__uint_as_float(sr[t + 1]), p.scale_log2e, -ls[t + 1]));
+                            d1 = p1 * (__uint_as_float(dr[t + 1]) - de[t + 1]);
+                        }
+                        pp[t >> 1] = pack_half2(p0, p1);
+                        dd[t >> 1] = pack_half2(d0, d1);
+                    }
+                }
+                // the dV / dK MMAs of the previous tile read the P^T / dS^T columns: done before these are overwritten
+                if (warp == 0) TL(i * 8 + 3 + (c >> 5) * 2);
+                if (i > 0) mbar_wait(&q_free[(i - 1) % ST], ((i - 1) / ST) & 1);
+                tmem_st_32x16(tm_pt + lane_off + (c >> 1), pp);
+                tmem_st_32x16(tm_dst + lane_off + (c >> 1), dd);
+            }
+            if (warp == 0) TL(i * 8 + 6);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_full);
+            if (warp == 0) TL(i * 8 + 7);
+            if (part == 0 && r < BQ && i + 1 < n_tiles) {
+                float* nb = sStat + ((i + 1) & 1) * 2 * BQ;
+                nb[r] = nl;
+                nb[BQ + r] = nd;
+            }
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        __half* ov = p.dv + (static_cast<long long>(img) * p.Nk + k0 + r) * p.lddv + head * p.d;
+        __half* okk = p.dk + (static_cast<long long>(img) * p.Nk + k0 + r) * p.lddk + head * p.d;
+        const float osc = part == 0 ? 1.0f : p.scale;  // part 0 stores dV, part 1 stores dK (scaled by d^-1/2)
+        __half* orow = part == 0 ? ov : okk;
+        const uint32_t tsrc = (part == 0 ? tm_dv : tm_dk) + lane_off;
+#pragma unroll
+        for (int c = 0; c < DPAD; c += 16) {
+            if (c < p.d) {
+                uint32_t rv[16];
+                tmem_ld_32x16(tsrc + c, rv);
+                tmem_ld_wait();
+                if (key_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (c + g * 8 < p.d) {
+                            uint4 u;
+                            uint32_t* uu = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                uu[e] = pack_half2(__uint_as_float(rv[g * 8 + 2 * e]) * osc, __uint_as_float(rv[g * 8 + 2 * e + 1]) * osc);
+                            *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int launch_dkdv_ts(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                          const AttnBwdParams& p, dim3 grid, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_bwd_dkdv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvTsSmem::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    return launch_pdl(attn_bwd_dkdv_ts_kernel, grid, dim3(DKV_TS_THREADS), (size_t)DkvTsSmem::TOTAL, s, tq, tdo, tk, tv, p) == cudaSuccess
+               ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
 template <int DPAD, int BKV>
 static int launch_dq(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
                      const AttnBwdParams& p, dim3 grid, cudaStream_t s) {
@@ -656,7 +917,13 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
         if (rc) return rc;
         p.idesc_s = umma_idesc_f16(128, bq, 0);
         dim3 grid((nk + 127) / 128, heads, batch);
-        if (d <= 48) rc = launch_dkdv<48, 64>(tq, tdo, tk, tv, p, grid, stream);
+        static int ts_env = -1;
+        if (ts_env < 0) {
+            const char* e = getenv("CTRLORA_ATTN_BWD_TS");
+            ts_env = (e && e[0] == '0') ? 0 : 1;  // 0: the two-CTAs-per-SM shared-memory-operand kernel (kept for A/B runs)
+        }
+        if (d <= 48 && ts_env && nk >= 512) rc = launch_dkdv_ts(tq, tdo, tk, tv, p, grid, stream);
+        else if (d <= 48) rc = launch_dkdv<48, 64>(tq, tdo, tk, tv, p, grid, stream);
         else if (d <= 80) rc = launch_dkdv<80, 128>(tq, tdo, tk, tv, p, grid, stream);
         else rc = launch_dkdv<160, 64>(tq, tdo, tk, tv, p, grid, stream);
         if (rc) return rc;
