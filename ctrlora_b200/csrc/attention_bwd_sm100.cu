@@ -565,6 +565,206 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+// ================================================================================================ dQ, all-TMEM
+// Same recipe as the all-TMEM dK/dV kernel below, for d <= 48 and long key sequences: one 512-column CTA per SM,
+// S / dP double-buffered, Q / dO / dS in TMEM, 8 row-math warps (two per TMEM lane group, one 32-key half each).
+//   columns: S0 64 | dP0 64 | S1 64 | dP1 64 | dQ 48 | dS 32 | Q 24 | dO 24 = 384.
+struct DqTsSmem {
+    static constexpr int BKV = 64, ST = 4;
+    static constexpr int Q_BYTES = 128 * 128;           // Q and dO: [128 queries][128 B]
+    static constexpr int KV_BYTES = BKV * 128;          // K and V tile: [64 keys][128 B]
+    static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+    static constexpr int OFF_DO = Q_BYTES, OFF_K = 2 * Q_BYTES;
+    static constexpr int DATA = OFF_K + ST * STAGE_BYTES;
+    static constexpr int TOTAL = DATA + 1024 + 256;
+};
+
+constexpr int DQ_TS_THREADS = 320;  // warps 0-7: row math, 8: TMA, 9: MMA
+
+__global__ void __launch_bounds__(DQ_TS_THREADS, 1)
+attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ AttnBwdParams p) {
+    using L = DqTsSmem;
+    constexpr int BKV = L::BKV, ST = L::ST, DPAD = 48, KS = DPAD / 16;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem, *sDO = smem + L::OFF_DO;
+    auto sK = [&](int st) { return smem + L::OFF_K + st * L::STAGE_BYTES; };
+    auto sV = [&](int st) { return smem + L::OFF_K + st * L::STAGE_BYTES + L::KV_BYTES; };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::DATA);
+    uint64_t *q_full = bars, *kv_full = bars + 1 /*[4]*/, *kv_free = bars + 5 /*[4]*/, *s_full = bars + 9 /*[2]*/, *ds_full = bars + 11,
+             *acc_done = bars + 12, *a_ready = bars + 13;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    if (warp == 9 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_free[i], 1); }
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(ds_full, 256); mbar_init(acc_done, 1); mbar_init(a_ready, 256);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tm_sdp = tmem_base;                 // buffer b: S at + 128 b, dP at + 128 b + 64
+    const uint32_t tm_dq = tmem_base + 256, tm_ds16 = tm_dq + DPAD, tm_q16 = tm_ds16 + BKV / 2, tm_do16 = tm_q16 + DPAD / 2;
+    const int n_tiles = (p.Nk + BKV - 1) / BKV;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * 128 * 128);
+            tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, img);
+            tma_load_4d(sDO, &tmDO, q_full, 0, head, q0, img);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j % ST;
+                if (j >= ST) mbar_wait(&kv_free[st], ((j / ST) - 1) & 1);
+                mbar_expect_tx(&kv_full[st], 2 * BKV * 128);
+                tma_load_4d(sK(st), &tmK, &kv_full[st], 0, head, j * BKV, img);
+                tma_load_4d(sV(st), &tmV, &kv_full[st], 0, head, j * BKV, img);
+            }
+        }
+    } else if (warp == 9) {
+        const uint32_t idesc_s = p.idesc_s, idesc_acc = p.idesc_acc;
+        auto issue_s_dp = [&](int j) {  // S = Q K(j)^T, dP = dO V(j)^T into buffer j & 1
+            const int st = j % ST;
+            mbar_wait(&kv_full[st], (j / ST) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dK = umma_desc_kmajor_sw128(smem_u32(sK(st))), dV = umma_desc_kmajor_sw128(smem_u32(sV(st)));
+                const uint32_t ts = tm_sdp + 128 * (j & 1);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) umma_f16_ts(ts, tm_q16 + 8 * ks, dK + 2 * ks, idesc_s, ks ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) umma_f16_ts(ts + 64, tm_do16 + 8 * ks, dV + 2 * ks, idesc_s, ks ? 1u : 0u);
+                umma_commit(&s_full[j & 1]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(a_ready, 0);  // Q / dO rows are in TMEM
+        issue_s_dp(0);
+        if (n_tiles > 1) issue_s_dp(1);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % ST;
+            mbar_wait(ds_full, j & 1);  // dS(j) is in TMEM; buffer j & 1 of S / dP has been read out
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t dKm = desc_mn_sw128(smem_u32(sK(st)), BKV * 128);
+                const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int ks = 0; ks < BKV / 16; ++ks)  // contraction over the keys of this tile
+                    umma_f16_ts(tm_dq, tm_ds16 + 8 * ks, dKm + ((ks * 2048) >> 4), idesc_acc, (acc | ks) ? 1u : 0u);
+                umma_commit(&kv_free[st]);  // K / V stage and the dS columns are free once these complete
+                if (j + 1 == n_tiles) umma_commit(acc_done);
+            }
+            __syncwarp();
+            if (j + 2 < n_tiles) issue_s_dp(j + 2);
+        }
+    } else {
+        const int lg = warp & 3, part = warp >> 2;  // TMEM lane group; 32-key half of every tile
+        const int r = lg * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lg * 32) << 16;
+        const bool row_ok = q0 + r < p.Nq;
+        const long long stat_idx = (static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r;
+        const float lse = row_ok ? p.lse[stat_idx] : 0.f;
+        const float dl = row_ok ? p.delta[stat_idx] : 0.f;
+        {
+            // this query's Q (part 0) / dO (part 1) row -> TMEM (SWIZZLE_128B tile: unit u sits at u ^ (r & 7))
+            mbar_wait(q_full, 0);
+            const uint32_t src = smem_u32(part == 0 ? sQ : sDO) + r * 128;
+            const uint32_t dst = (part == 0 ? tm_q16 : tm_do16) + lane_off;
+            uint32_t w[24];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const uint4 x = lds128(src + ((u ^ (r & 7)) << 4));
+                w[4 * u] = x.x; w[4 * u + 1] = x.y; w[4 * u + 2] = x.z; w[4 * u + 3] = x.w;
+            }
+            tmem_st_32x16(dst, w);
+            tmem_st_32x8(dst + 16, w + 16);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(a_ready);
+        }
+        const int c = 32 * part;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const int kv_valid = min(BKV, p.Nk - j * BKV);
+            const uint32_t ts = tm_sdp + 128 * (j & 1) + lane_off;
+            uint32_t sr[32], dr[32], packed[16];
+            tmem_ld_32x32(ts + c, sr);
+            tmem_ld_32x32(ts + 64 + c, dr);
+            tmem_ld_wait();
+            if (kv_valid == BKV) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse));
+                    packed[i >> 1] = pack_half2(p0 * (__uint_as_float(dr[i]) - dl), p1 * (__uint_as_float(dr[i + 1]) - dl));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float ds0 = 0.f, ds1 = 0.f;
+                    if (c + i < kv_valid) ds0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2e, -lse)) * (__uint_as_float(dr[i]) - dl);
+                    if (c + i + 1 < kv_valid) ds1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2e, -lse)) * (__uint_as_float(dr[i + 1]) - dl);
+                    packed[i >> 1] = pack_half2(ds0, ds1);
+                }
+            }
+            // the dQ MMAs of the previous tile read the dS columns: done before they are overwritten
+            if (j > 0) mbar_wait(&kv_free[(j - 1) % ST], ((j - 1) / ST) & 1);
+            tmem_st_32x16(tm_ds16 + lane_off + (c >> 1), packed);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(ds_full);
+        }
+        mbar_wait(acc_done, 0);
+        tc_fence_after();
+        __half* out = p.dq + (static_cast<long long>(img) * p.Nq + q0 + r) * p.lddq + head * p.d;
+#pragma unroll
+        for (int cc = 0; cc < DPAD; cc += 16) {
+            if (cc < p.d && ((cc >> 4) & 1) == part) {
+                uint32_t raw[16];
+                tmem_ld_32x16(tm_dq + lane_off + cc, raw);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (cc + g * 8 < p.d) {
+                            uint4 u;
+                            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                w[e] = pack_half2(__uint_as_float(raw[g * 8 + 2 * e]) * p.scale, __uint_as_float(raw[g * 8 + 2 * e + 1]) * p.scale);
+                            *reinterpret_cast<uint4*>(out + cc + g * 8) = u;
+                        }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int launch_dq_ts(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const AttnBwdParams& p, dim3 grid, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attn_bwd_dq_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqTsSmem::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    return launch_pdl(attn_bwd_dq_ts_kernel, grid, dim3(DQ_TS_THREADS), (size_t)DqTsSmem::TOTAL, s, tq, tdo, tk, tv, p) == cudaSuccess
+               ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
 // ================================================================================================ dK, dV, all-TMEM
 // d <= 48 (the 64x64 level: almost all of the backward attention time). One CTA per SM with the whole 512-column TMEM:
 //   S^T / dP^T double-buffered (2 x 128 columns): the products of query tile i+1 (and i+2) are computed while the row
@@ -901,7 +1101,13 @@ extern "C" int ctrlora_attention_bwd_f16(const void* q, long long ldq, const voi
         if (rc) return rc;
         p.idesc_s = umma_idesc_f16(128, bkv, 0);
         dim3 grid((nq + 127) / 128, heads, batch);
-        if (d <= 48) rc = launch_dq<48, 64>(tq, tdo, tk, tv, p, grid, stream);
+        static int tsq_env = -1;
+        if (tsq_env < 0) {
+            const char* e = getenv("CTRLORA_ATTN_BWD_TS");
+            tsq_env = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (d <= 48 && tsq_env && nk >= 512) rc = launch_dq_ts(tq, tdo, tk, tv, p, grid, stream);
+        else if (d <= 48) rc = launch_dq<48, 64>(tq, tdo, tk, tv, p, grid, stream);
         else if (d <= 80) rc = launch_dq<80, 128>(tq, tdo, tk, tv, p, grid, stream);
         else rc = launch_dq<160, 64>(tq, tdo, tk, tv, p, grid, stream);
         if (rc) return rc;
