@@ -324,6 +324,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 //     columns and P V is issued in the A-from-TMEM form, which costs N/2 = 24 cycles per k-step instead of the
 //     32 + N/4 = 44 of the smem-A form (tools/microbench/mma_issue.cu: the smem A read is the floor for small N).
 constexpr float ATT_TAU = 8.0f;
+// Every 2*k-th exponential of the fast path can run on the FMA pipe (exp2_poly3). Measured at 4096 x 4096, d = 40: 0 -> 444 us,
+// 1/8 -> 443 us, 1/4 -> 452 us, 1/2 -> 522 us: the kernel is issue/latency-bound before it is MUFU-bound, so it is off.
+#ifndef CTRLORA_ATT_POLY_EVERY
+#define CTRLORA_ATT_POLY_EVERY 0
+#endif
+constexpr int ATT_POLY_EVERY = CTRLORA_ATT_POLY_EVERY;
 
 template <int DPAD>
 struct StreamSmem {
@@ -351,7 +357,8 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&raw)[32], float s
         for (int i = 0; i < 32; i += 2) {
             tmax = max3f(tmax, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
             const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, neg));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(raw[i + 1]), sl2, neg));
+            const float x1 = fmaf(__uint_as_float(raw[i + 1]), sl2, neg);
+            const float p1 = (ATT_POLY_EVERY > 0 && ((i >> 1) % ATT_POLY_EVERY) == ATT_POLY_EVERY - 1) ? exp2_poly3(x1) : fast_exp2(x1);
             packed[i >> 1] = pack_half2(p0, p1);
         }
     } else {
