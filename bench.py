@@ -377,8 +377,9 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): per-launch CUDA events on an un-graphed step
-    gemm_stats = ops.profile_gemm(lambda: step(0, dev["x"]), sampler)
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): the step's GEMM launches are recorded on an
+    # un-graphed step, then replayed back to back from one CUDA graph between two CUDA events (ops.replay_gemms)
+    gemm_stats = ops.replay_gemms(lambda: step(0, dev["x"]), sampler)
 
     t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
@@ -403,7 +404,8 @@ def main():
                 "gpu_launches": launches_per_step * args.steps,
                 "images_per_sec": value * BATCH,
                 "model_tflops": value / world * 2 * BATCH * GF_PER_IMAGE_PASS / 1e3,
-                "roofline": {"kernel": "gemm_tcgen05_kernel (all convs + linears of one step)", "bound": "tensor",
+                "roofline": {"kernel": "gemm_tcgen05_kernel (all convs + linears of one step, replayed back to back from a CUDA graph)",
+                             "bound": "tensor",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                              "peak_source": peak_src + ", sustained bf16/fp16 dense", "traffic": None,
                              "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,

@@ -14,6 +14,7 @@ from ._lib import GemmArgs, check
 LAUNCHES = 0      # kernels launched through this module since the last reset (bench.py's gpu_launches)
 _GEMM_PROFILE = None  # list of (flops, start_event, end_event) while profile_gemm() is active
 _GEMM_SHAPES = None   # optional parallel list of problem shapes (tools/profile_step.py)
+_GEMM_RECORD = None   # list of (args struct, flops, keep-alive tensors) while replay_gemms() records a step
 
 
 def _count(n=1):
@@ -52,6 +53,49 @@ def profile_gemm(fn, sampler=None):
         _GEMM_PROFILE = None
     return {"launches": len(recs), "flops": float(sum(r[0] for r in recs)),
             "ms": float(sum(r[1].elapsed_time(r[2]) for r in recs))}
+
+
+def replay_gemms(fn, sampler=None, reps=5):
+    """Device time of the GEMM launches of `fn` replayed back to back from one CUDA graph.
+
+    `fn` runs once un-graphed while every ctrlora_gemm_f16 argument block is recorded (its tensors are kept alive), then
+    exactly those launches are captured into a graph and replayed `reps` times between two CUDA events on the capture
+    stream.  Unlike per-launch events on an un-graphed step (host-bound: the GPU idles between launches, clocks and L2
+    state differ from the real run) this times the kernels under the conditions they run in: PDL-chained, warm clocks.
+    Returns {"launches", "flops", "ms"} for ONE pass over the step's GEMMs."""
+    global _GEMM_RECORD
+    _GEMM_RECORD = []
+    try:
+        _ungraphed(fn, sampler)
+        recs = _GEMM_RECORD
+    finally:
+        _GEMM_RECORD = None
+    lib = _lib.load()
+
+    def launch_all():
+        sp = _sp()
+        for args, _, _ in recs:
+            check(lib.ctrlora_gemm_f16(C.addressof(args), sp), "ctrlora_gemm_f16 (replay)")
+
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        launch_all()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            launch_all()
+        graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+    torch.cuda.current_stream().wait_stream(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"launches": len(recs), "flops": float(sum(r[1] for r in recs)), "ms": float(ms)}
+    del graph, recs
+    return out
 
 
 _SPLITK = {}  # device index -> (fp32 workspace, uint32 counters); zero on entry and on exit of every GEMM launch
@@ -150,6 +194,10 @@ def gemm(a, w, *, ksize=1, bias=None, rowbias=None, rows_per_img=0, rowbias_ld=0
     lib = _lib.load()
     fn = lib.ctrlora_gemm_f16_simt if simt else lib.ctrlora_gemm_f16
     _count()
+    if _GEMM_RECORD is not None and not simt:
+        ktot = ksize * ksize * c + (args.a2_c if a2 is not None else 0)
+        _GEMM_RECORD.append((args, 2.0 * M * n_rows * ktot,
+                             (a, w, a2, w2, bias, rowbias, residual, out, seg_outs, dup_out, ws, cnt)))
     if _GEMM_PROFILE is not None and not simt:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
