@@ -525,8 +525,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // ---- split-K: park this split's partial tile in its own fp32 workspace slice (plain stores)
                 const int tile_mn = nt * m_tiles + mt;
                 const long long slice = static_cast<long long>(GEMM_BM) * p.BN;
-                float* wrow0 = p.ws + static_cast<long long>(tile_mn) * p.splits * slice + static_cast<long long>(r) * p.BN;
+                // slice layout [BN / 4][128 rows][4 floats]: thread = row, so the 32 lanes of a warp touch 32 consecutive
+                // 16-byte slots (512 contiguous bytes per instruction) both when parking and when reducing
+                float* wrow0 = p.ws + static_cast<long long>(tile_mn) * p.splits * slice + static_cast<long long>(r) * 4;
                 float* wrow = wrow0 + ks * slice;
+                auto wofs = [](int col) { return static_cast<long long>(col >> 2) * (GEMM_BM * 4); };
                 for (int c = 32 * half; c < p.BN; c += 64) {
                     uint32_t raw[32];
                     tmem_ld_32x32(t_row + c, raw);
@@ -534,7 +537,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if (c + 4 * q < p.BN)
-                            __stcg(reinterpret_cast<float4*>(wrow + c + 4 * q),
+                            __stcg(reinterpret_cast<float4*>(wrow + wofs(c + 4 * q)),
                                    make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
                                                __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3])));
                 }
@@ -560,10 +563,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = t4;
                             if (c + 4 * q < bn_out) {
                                 for (int sl = 0; sl < p.splits; ++sl) {  // fixed order: deterministic sums
-                                    const float4 x4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + c + 4 * q));
+                                    const float4 x4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + wofs(c + 4 * q)));
                                     t4.x += x4.x; t4.y += x4.y; t4.z += x4.z; t4.w += x4.w;
                                     if (GEGLU) {
-                                        const float4 y4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + bn_out + c + 4 * q));
+                                        const float4 y4 = __ldcg(reinterpret_cast<const float4*>(wrow0 + sl * slice + wofs(bn_out + c + 4 * q)));
                                         g4.x += y4.x; g4.y += y4.y; g4.z += y4.z; g4.w += y4.w;
                                     }
                                 }

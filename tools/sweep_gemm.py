@@ -9,13 +9,15 @@ sys.path.insert(0, ROOT)
 from ctrlora_b200 import ops  # noqa: E402
 from tools.profile_kernels import rnd, timeit  # noqa: E402
 
+import os as _os
+SHAPES_SMALL = [(8, 8, 8, 1280, 1280, 3), (8, 8, 8, 2560, 1280, 3), (8, 8, 8, 1280, 1280, 1), (8, 16, 16, 1280, 1280, 3), (8, 16, 16, 1280, 1280, 1)]
 SHAPES = [  # B, H, W, C, N, ksize
     (8, 8, 8, 1280, 1280, 3), (8, 16, 16, 1280, 1280, 3), (8, 16, 16, 1280, 1280, 1), (8, 32, 32, 640, 640, 1),
     (8, 64, 64, 320, 320, 1), (8, 8, 8, 1280, 1280, 1), (8, 16, 16, 2560, 1280, 3), (8, 32, 32, 640, 640, 3),
     (8, 64, 64, 320, 320, 3), (8, 32, 32, 1920, 640, 3), (8, 64, 64, 960, 320, 3), (8, 64, 64, 640, 320, 3),
 ]
 if __name__ == "__main__":
-    for (b, h, w, c, n, ks) in SHAPES:
+    for (b, h, w, c, n, ks) in (SHAPES_SMALL if _os.environ.get('SWEEP_SMALL') else SHAPES):
         a, wt = rnd(b, h, w, c), rnd(n, ks * ks, c, scale=(ks * ks * c) ** -0.5)
         bias, res = torch.randn(n, device="cuda"), rnd(b * h * w, n)
         out = torch.empty(b, h, w, n, device="cuda", dtype=torch.float16)
