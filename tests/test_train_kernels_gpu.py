@@ -140,7 +140,8 @@ def test_mse_loss_and_adamw():
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 512, 512, 40), (1, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (2, 8, 256, 77, 40),
-                                         (2, 4, 200, 300, 16), (1, 8, 64, 64, 160), (2, 8, 1024, 77, 80), (1, 4, 130, 129, 32)])
+                                         (2, 4, 200, 300, 16), (1, 8, 64, 64, 160), (2, 8, 1024, 77, 80), (1, 4, 130, 129, 32),
+                                         (1, 8, 600, 700, 40), (1, 2, 520, 1000, 24), (1, 2, 640, 576, 48)])  # all-TMEM kernels, ragged
 def test_attention_backward(B, H, Nq, Nk, d):
     """dQ, dK, dV of the fused attention against torch autograd on the same fp16-rounded inputs."""
     from ctrlora_b200 import ops
