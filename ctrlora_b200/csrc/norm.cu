@@ -84,7 +84,7 @@ gn_stats_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __
     }
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)  // <= 64 registers: four 240..256-thread blocks per SM, the whole grid in one wave
 gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                 __half* __restrict__ y, __half* __restrict__ raw) {
@@ -130,12 +130,12 @@ gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const flo
         *reinterpret_cast<uint4*>(y + pix * C + vec * 8) = u;
     };
     int p = p0 + pl;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {
-        float v[4][8];
+    for (; p + lanes < p1; p += 2 * lanes) {  // two vectors in flight per thread, four blocks per SM
+        float v[2][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load8(s, static_cast<long long>(b) * HW + p + u * lanes, vec * 8, v[u]);
+        for (int u = 0; u < 2; ++u) load8(s, static_cast<long long>(b) * HW + p + u * lanes, vec * 8, v[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) emit(static_cast<long long>(b) * HW + p + u * lanes, v[u]);
+        for (int u = 0; u < 2; ++u) emit(static_cast<long long>(b) * HW + p + u * lanes, v[u]);
     }
     for (; p < p1; p += lanes) {
         float v[8];
@@ -296,17 +296,31 @@ gn_bwd_stats_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int g
             mu[e] = mean; rs[e] = rsqrtf(var + eps); ga[e] = gamma[c]; be[e] = beta[c]; a[e] = 0.f; q[e] = 0.f;
         }
         const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-        for (int p = p0 + pl; p < p1; p += lanes) {
-            const long long pix = static_cast<long long>(b) * HW + p;
-            float x[8], d[8];
-            load8(s, pix, vec * 8, x);
-            load8h(dy + pix * C + vec * 8, d);
+        auto accum = [&](const float* x, const float* d) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float xh = (x[e] - mu[e]) * rs[e];
                 const float dz = silu ? d[e] * dsilu_f(xh * ga[e] + be[e]) : d[e];
                 a[e] += dz; q[e] += dz * xh;
             }
+        };
+        int p = p0 + pl;
+        for (; p + lanes < p1; p += 2 * lanes) {  // two pixels (four 16-byte loads) in flight per thread
+            const long long pix = static_cast<long long>(b) * HW + p;
+            float x0[8], d0[8], x1[8], d1[8];
+            load8(s, pix, vec * 8, x0);
+            load8h(dy + pix * C + vec * 8, d0);
+            load8(s, pix + lanes, vec * 8, x1);
+            load8h(dy + (pix + lanes) * C + vec * 8, d1);
+            accum(x0, d0);
+            accum(x1, d1);
+        }
+        for (; p < p1; p += lanes) {
+            const long long pix = static_cast<long long>(b) * HW + p;
+            float x[8], d[8];
+            load8(s, pix, vec * 8, x);
+            load8h(dy + pix * C + vec * 8, d);
+            accum(x, d);
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) { atomicAdd(&c_dz[vec * 8 + e], a[e]); atomicAdd(&c_dzx[vec * 8 + e], q[e]); }
@@ -352,7 +366,37 @@ gn_bwd_apply_kernel(GnSrc s, const __half* __restrict__ dy, int C, int HW, int g
     const int coff = first ? vec * 8 : vec * 8 - s.c1;
     const float osc = first ? scale1 : scale2;
     const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-    for (int p = p0 + pl; p < p1; p += lanes) {
+    auto one = [&](long long pix, const float* x, const float* d, const float* rr) {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float xh = (x[e] - mu[e]) * rs[e];
+            const float dz = silu ? d[e] * dsilu_f(xh * ga[e] + be[e]) : d[e];
+            o[e] = (rs[e] * (dz * ga[e] - m1[e] - xh * m2[e]) + rr[e]) * osc;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+        *reinterpret_cast<uint4*>(dst + pix * ldd + coff) = u;
+    };
+    int p = p0 + pl;
+    for (; p + lanes < p1; p += 2 * lanes) {  // two pixels in flight per thread
+        const long long pix = static_cast<long long>(b) * HW + p;
+        float x0[8], d0[8], x1[8], d1[8];
+        float r0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        load8(s, pix, vec * 8, x0);
+        load8h(dy + pix * C + vec * 8, d0);
+        load8(s, pix + lanes, vec * 8, x1);
+        load8h(dy + (pix + lanes) * C + vec * 8, d1);
+        if (res) {  // gradient arriving over the block's skip path (identity residual or the 1x1 skip conv's dgrad)
+            load8h(res + pix * ldres + vec * 8, r0);
+            load8h(res + (pix + lanes) * ldres + vec * 8, r1);
+        }
+        one(pix, x0, d0, r0);
+        one(pix + lanes, x1, d1, r1);
+    }
+    for (; p < p1; p += lanes) {
         const long long pix = static_cast<long long>(b) * HW + p;
         float x[8], d[8];
         load8(s, pix, vec * 8, x);
