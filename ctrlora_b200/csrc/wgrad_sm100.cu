@@ -53,7 +53,7 @@ wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* empty = bars + WG_STAGES;
     uint64_t* tfull = bars + 2 * WG_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -92,28 +92,33 @@ wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = it0; it < it1; ++it) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + stage * p.stage_bytes);
-                const uint32_t b_addr = a_addr + WG_A_BYTES;
+        // whole warp in the loop, one elected lane issues; descriptors advance by adds in the 16-byte address field
+        const uint64_t dA0 = umma_desc_mnmajor_sw128(smem_u32(smem), WG_BK * 128);
+        const uint64_t dB0 = umma_desc_mnmajor_sw128(smem_u32(smem) + WG_A_BYTES, WG_BK * 128);
+        const uint32_t idesc = p.idesc, stage_step = static_cast<uint32_t>(p.stage_bytes) >> 4;
+        int stage = 0;
+        uint32_t phase = 0, off = 0, acc = 0;
+        for (int it = it0; it < it1; ++it) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < WG_BK / 16; ++k) {  // 16 tokens per MMA = two 8-token groups = 2048 B
-                    umma_f16(tmem_base, umma_desc_mnmajor_sw128(a_addr + k * 2048, WG_BK * 128),
-                             umma_desc_mnmajor_sw128(b_addr + k * 2048, WG_BK * 128), p.idesc, (it > it0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < WG_BK / 16; ++k)  // 16 tokens per MMA = two 8-token groups = 2048 B
+                    umma_f16(tmem_base, dA0 + off + k * 128, dB0 + off + k * 128, idesc, (acc | k) ? 1u : 0u);
                 umma_commit(&empty[stage]);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (it + 1 == it1) umma_commit(tfull);
             }
-            umma_commit(tfull);
+            __syncwarp();
+            acc = 1;
+            off += stage_step;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; off = 0; }
         }
     } else {
         const int lane_grp = warp & 3;
         const int r = lane_grp * 32 + lane;  // row of the P tile
-        float* dst = p.ws + (static_cast<long long>(split) * p.p_tiles * 128 + p0 + r) * (static_cast<long long>(p.q_tiles) * p.q_tile) + q0;
+        // slice layout [Q_pad / 4][P_pad rows][4 floats]: the 32 lanes (rows) of a warp write 512 contiguous bytes
+        const long long P_pad = static_cast<long long>(p.p_tiles) * 128, Q_pad = static_cast<long long>(p.q_tiles) * p.q_tile;
+        float* dst = p.ws + static_cast<long long>(split) * P_pad * Q_pad + (static_cast<long long>(q0 >> 2) * P_pad + p0 + r) * 4;
         if (it1 > it0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
@@ -124,11 +129,13 @@ wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    reinterpret_cast<float4*>(dst + c)[q] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]),
-                                                                        __uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+                    *reinterpret_cast<float4*>(dst + (static_cast<long long>((c >> 2) + q) * P_pad) * 4) =
+                        make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                                    __uint_as_float(raw[4 * q + 3]));
             }
         } else {  // empty split (token count not divisible): contribute zeros
-            for (int c = 0; c < p.q_tile; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < p.q_tile; c += 4)
+                *reinterpret_cast<float4*>(dst + (static_cast<long long>(c >> 2) * P_pad) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     tc_fence_before();
@@ -141,14 +148,23 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
                                     int splits, long long ldo, float alpha, float beta) {
     pdl_launch_dependents();
     pdl_wait();
+    // thread = (4 columns, row), rows fastest: the slice reads are 512 contiguous bytes per warp
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<long long>(P) * Q) return;
-    const int q = static_cast<int>(i % Q);
-    const int pr = static_cast<int>(i / Q);
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[(static_cast<long long>(s) * P_pad + pr) * Q_pad + q];
-    float* o = out + pr * ldo + q;
-    *o = alpha * acc + (beta != 0.f ? beta * *o : 0.f);
+    const int q4s = Q >> 2;  // Q is a multiple of 8
+    if (i >= static_cast<long long>(P) * q4s) return;
+    const int pr = static_cast<int>(i % P);
+    const int q4 = static_cast<int>(i / P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long slice = static_cast<long long>(P_pad) * Q_pad;
+    const float* src = ws + (static_cast<long long>(q4) * P_pad + pr) * 4;
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(src + s * slice);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* o = out + pr * ldo + 4 * q4;
+    if (beta != 0.f) { acc.x = alpha * acc.x + beta * o[0]; acc.y = alpha * acc.y + beta * o[1]; acc.z = alpha * acc.z + beta * o[2]; acc.w = alpha * acc.w + beta * o[3]; }
+    else { acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha; }
+    o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
 }
 
 }  // namespace ctrl
@@ -174,8 +190,8 @@ extern "C" int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // enough token splits to fill the machine about twice, at least 8 k-iterations each, within the workspace
-    int splits = (2 * sms + p.p_tiles * p.q_tiles - 1) / (p.p_tiles * p.q_tiles);
+    // enough token splits to fill the machine once, at least 8 k-iterations each, within the workspace
+    int splits = (sms + p.p_tiles * p.q_tiles - 1) / (p.p_tiles * p.q_tiles);  // one wave: half the workspace traffic of two
     if (splits > k_total / 8) splits = k_total / 8;
     if (splits < 1) splits = 1;
     const long long slice = static_cast<long long>(p.p_tiles) * 128 * p.q_tiles * p.q_tile * 4;
@@ -210,7 +226,7 @@ extern "C" int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b,
     if (launch_pdl(wgrad_tn_kernel, dim3(p.p_tiles * p.q_tiles, p.splits), dim3(WG_THREADS), (size_t)smem_bytes, stream, tmA,
                    tmB, p) != cudaSuccess)
         return CTRLORA_ERR_CUDA;
-    const long long total = static_cast<long long>(p_dim) * q_dim;
+    const long long total = static_cast<long long>(p_dim) * (q_dim / 4);
     if (launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, stream,
                    (const float*)ws, out, p_dim, q_dim, p.p_tiles * 128, p.q_tiles * p.q_tile, p.splits, ldo, alpha, beta) !=
         cudaSuccess)
