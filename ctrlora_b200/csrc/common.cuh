@@ -235,20 +235,40 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// exact-erf GELU (F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below fp16 rounding):
-// one exp and six FMAs instead of libdevice erff's ~40 branchy instructions -- the GEGLU epilogue is math-bound.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sigmoid / SiLU on raw ex2 / rcp (the __expf / __fdividef intrinsics add range-fixup FSETP / FMUL / FSEL sequences:
+// ncu counted 38 instructions per GEGLU output element with them, see profiles/README.md)
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + fast_exp2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// exact-erf GELU (F.gelu default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below fp16 rounding).
+// erf_as(x) for the backward; gelu_erf_f is the fused forward form:
+//   gelu(x) = max(x, 0) - |x|/2 * w(|x|),  w(a) = poly(t) * t * exp(-a^2/2),  t = 1 / (1 + p a / sqrt 2)
+// with the 1/sqrt(2) and log2(e) factors folded into the constants: 2 MUFU + 13 FMA-pipe instructions, no selects.
 __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float y = 1.0f - poly * t * __expf(-ax * ax);
+    const float y = 1.0f - poly * t * fast_exp2(-1.4426950408889634f * ax * ax);
     return copysignf(y, x);
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_f(float x) {
+    const float z = x * 0.84932180028801904f;            // x / sqrt(2) * sqrt(log2 e)
+    const float e = fast_exp2(-z * z);                    // exp(-x^2 / 2)
+    const float t = fast_rcp(fmaf(0.27273706287f, fabsf(z), 1.0f));  // 1 / (1 + 0.3275911 |x| / sqrt 2)
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float w = poly * t * e;                         // 1 - erf(|x| / sqrt 2)
+    return fmaf(-0.5f * fabsf(x), w, fmaxf(x, 0.0f));
+}
 
 }  // namespace ctrl
 

@@ -259,7 +259,7 @@ extern "C" int ctrlora_layernorm_f16(const void* x, long long ldx, void* y, long
 namespace ctrl {
 
 __device__ __forceinline__ float dsilu_f(float z) {
-    const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+    const float s = sigmoid_f(z);
     return s * (1.0f + z * (1.0f - s));
 }
 
