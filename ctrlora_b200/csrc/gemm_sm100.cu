@@ -713,7 +713,12 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     } else if (a->transposed[0] || a->dup_out) {
         epi_legal = false;
     }
-    const bool epi_wanted = epi_legal && (epi_env == 2 || (epi_env == 1 && k_iters <= 32));
+    static int epi_kmax = -1;
+    if (epi_kmax < 0) {
+        const char* e = getenv("CTRLORA_GEMM_EPI_KMAX");
+        epi_kmax = e ? atoi(e) : 32;
+    }
+    const bool epi_wanted = epi_legal && (epi_env == 2 || (epi_env == 1 && k_iters <= epi_kmax));
     int bn_out = a->block_n, splits = a->split_k > 0 ? a->split_k : 1;
     if (bn_out <= 0) {
         double best_cost = -1;
