@@ -691,7 +691,7 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     }
     // Measured (profiles/README.md): pairs win where the k loop dominates (3x3 convs and K >= 1024 linears: -10..-30 %),
     // lose on short-K 1x1 / GEGLU tiles whose time is the epilogue.
-    const bool pair_shape = pair_env == 2 || (!p.geglu && k_iters >= (p.taps > 1 ? 24 : 16));
+    const bool pair_shape = pair_env == 2 || (!p.geglu && k_iters >= (p.taps > 1 ? 24 : 16)) || (p.geglu && k_iters >= 20);
     const bool pair_ok = pair_env && pair_shape && g_num_sms >= 2 && a->force_single_cta == 0;
     // ---- pick the N tile and the K split with a per-tile cycle model, in cycles at the ~1.45 GHz the
     // part holds under tensor load: a k-step costs max(MMA = 2 x BN, operand bytes / 69 B/clk (~100 GB/s per SM, the
