@@ -240,18 +240,28 @@ small_linear_staged_kernel(const float* __restrict__ x, int ldx, const __half* _
             float acc[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-            for (int k = lane * 8; k < K; k += 256) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k));
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
-                float wv[8];
+            // the whole weight row of this feature in flight at once (K <= 2048: eight 16-byte loads per lane)
+            uint4 uw[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); wv[2 * e] = f.x; wv[2 * e + 1] = f.y; }
+            for (int c = 0; c < 8; ++c) {
+                const int k = lane * 8 + c * 256;
+                uw[c] = k < K ? __ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k)) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (r0 + r < rows) {
-                        const float4 a = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k);
-                        const float4 b = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k + 4);
-                        acc[r] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + b.x * wv[4] + b.y * wv[5] + b.z * wv[6] + b.w * wv[7];
+            for (int c = 0; c < 8; ++c) {
+                const int k = lane * 8 + c * 256;
+                if (k < K) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&uw[c]);
+                    float wv[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); wv[2 * e] = f.x; wv[2 * e + 1] = f.y; }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (r0 + r < rows) {
+                            const float4 a = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k);
+                            const float4 b = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k + 4);
+                            acc[r] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + b.x * wv[4] + b.y * wv[5] + b.z * wv[6] + b.w * wv[7];
+                        }
                     }
                 }
             }
@@ -277,7 +287,7 @@ small_linear_staged_kernel(const float* __restrict__ x, int ldx, const __half* _
 extern "C" int ctrlora_small_linear(const float* x, int ldx, const void* w, const float* bias, float* y, int ldy,
                                     int rows, int n, int k, int silu_in, int silu_out, void* stream) {
     if (!x || !w || !y || k % 8 != 0 || ldx % 4 != 0) return CTRLORA_ERR_ARG;
-    if (static_cast<long long>(rows) * k <= 40960) {
+    if (static_cast<long long>(rows) * k <= 40960 && k <= 2048) {
         const size_t sm = static_cast<size_t>(rows) * k * sizeof(float);
         static bool attr = false;
         if (!attr) {
