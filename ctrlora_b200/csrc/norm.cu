@@ -218,7 +218,9 @@ extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stre
     s.x2 = reinterpret_cast<const __half*>(a->x2); s.add2 = reinterpret_cast<const __half*>(a->add2); s.s2 = a->add2_scale;
     s.c2 = a->x2 ? a->c2 : 0; s.ld2 = a->ld2;
     const int HW = a->hw, B = a->batch;
-    if (cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    if (!a->stats_prezeroed &&
+        cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
     // ~4 blocks per SM in total, at least 8 pixels per block
     int chunks = (592 + B - 1) / B;
     int ppb = (HW + chunks - 1) / chunks;
@@ -228,9 +230,13 @@ extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stre
     const int vecs = C / 8;
     const int lanes = vecs >= 256 ? 1 : 256 / vecs;
     const int threads = vecs * lanes;  // every thread owns one 8-channel vector of one pixel lane
-    // the stats kernel follows a memset node (plain launch); the apply kernel chains onto it programmatically
-    gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(s, C, HW, a->groups, ppb,
-                                                                 reinterpret_cast<float*>(a->stats_ws));
+    // after a memset node the stats kernel is a plain launch; with a pre-zeroed workspace it chains programmatically
+    if (a->stats_prezeroed)
+        launch_pdl(gn_stats_kernel, grid, dim3(threads), (size_t)(2 * C * sizeof(float)), stream, s, C, HW, (int)a->groups, ppb,
+                   reinterpret_cast<float*>(a->stats_ws));
+    else
+        gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(s, C, HW, a->groups, ppb,
+                                                                     reinterpret_cast<float*>(a->stats_ws));
     launch_pdl(gn_apply_kernel, grid, dim3(threads), (size_t)0, stream, s, C, HW, (int)a->groups, ppb,
                reinterpret_cast<const float*>(a->stats_ws), a->gamma, a->beta, a->eps, (int)a->silu,
                reinterpret_cast<__half*>(a->y), reinterpret_cast<__half*>(a->raw_out));
@@ -532,7 +538,9 @@ extern "C" int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* a, const 
     s.x2 = reinterpret_cast<const __half*>(a->x2); s.add2 = reinterpret_cast<const __half*>(a->add2); s.s2 = a->add2_scale;
     s.c2 = a->x2 ? a->c2 : 0; s.ld2 = a->ld2;
     const int HW = a->hw, B = a->batch;
-    if (cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess) return CTRLORA_ERR_CUDA;
+    if (!a->stats_prezeroed &&
+        cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
     int chunks = (592 + B - 1) / B;
     int ppb = (HW + chunks - 1) / chunks;
     if (ppb < 8) ppb = 8;
@@ -541,9 +549,14 @@ extern "C" int ctrlora_groupnorm_bwd_f16(const ctrlora_groupnorm_args* a, const 
     const int vecs = C / 8;
     const int lanes = vecs >= 256 ? 1 : 256 / vecs;
     const int threads = vecs * lanes;
-    gn_bwd_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
-        s, reinterpret_cast<const __half*>(dy), C, HW, a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), a->gamma,
-        a->beta, a->eps, a->silu, reinterpret_cast<float*>(a->stats_ws), dgamma, dbeta);
+    if (a->stats_prezeroed)
+        launch_pdl(gn_bwd_stats_kernel, grid, dim3(threads), (size_t)(2 * C * sizeof(float)), stream, s,
+                   reinterpret_cast<const __half*>(dy), C, HW, (int)a->groups, ppb, reinterpret_cast<const float*>(fwd_stats),
+                   a->gamma, a->beta, a->eps, (int)a->silu, reinterpret_cast<float*>(a->stats_ws), dgamma, dbeta);
+    else
+        gn_bwd_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
+            s, reinterpret_cast<const __half*>(dy), C, HW, a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), a->gamma,
+            a->beta, a->eps, a->silu, reinterpret_cast<float*>(a->stats_ws), dgamma, dbeta);
     launch_pdl(gn_bwd_apply_kernel, grid, dim3(threads), (size_t)0, stream, s, reinterpret_cast<const __half*>(dy), C, HW,
                (int)a->groups, ppb, reinterpret_cast<const float*>(fwd_stats), reinterpret_cast<const float*>(a->stats_ws),
                a->gamma, a->beta, a->eps, (int)a->silu, reinterpret_cast<__half*>(dx1), ldd1, dx1_scale,

@@ -5,6 +5,8 @@ import copy
 import torch
 import torch.nn as nn
 
+from ctrlora_b200 import ops
+
 from cldm.cldm import ControlLDM, ControlNet
 from cldm.ddim_hacked import DDIMSampler
 from cldm.lora import LoRACompatibleLinear, LoRALinearLayer
@@ -79,6 +81,7 @@ class ControlInferenceLDM(ControlLDM):
         shape = (self.channels, h // 8, w // 8) if c != self.channels else (self.channels, h, w)
         return sampler.sample(ddim_steps, batch_size, shape, cond, verbose=False, **kwargs)
 
+    @ops.with_stats_arena
     def apply_model(self, x_noisy, t, conds, *args, **kwargs):
         if isinstance(conds, dict):
             conds = [conds]

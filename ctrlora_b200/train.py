@@ -542,6 +542,7 @@ class FinetuneTrainer:
         """q_sample -> apply_model -> MSE -> backward into the flat gradient buffer.  Returns the loss (fp32 tensor)."""
         m = self.model
         self.G.zero()
+        ops.stats_arena_begin(x0.device)  # one memset for all GroupNorm forward / backward statistics of the step
         x_noisy = m.q_sample(x_start=x0, t=t, noise=noise)
         control, cn_saved = controlnet_fwd(self.cn, hint_latent, t, context)
         eps, un_saved = unet_fwd(self.unet, x_noisy, t, context, control, m.control_scales, m.only_mid_control)
@@ -550,6 +551,7 @@ class FinetuneTrainer:
         if m.only_mid_control:
             d_ctrl = [d if d is not None else torch.zeros_like(c) for d, c in zip(d_ctrl, control)]
         controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G)
+        ops.stats_arena_end(x0.device)
         self.last_eps = eps
         return loss
 

@@ -99,6 +99,8 @@ typedef struct ctrlora_groupnorm_args {
     void* y;          /* fp16 [batch*hw, c1+c2] */
     void* raw_out;    /* optional fp16 [batch*hw, c1+c2]: the concatenated (and summed) input itself, or NULL */
     void* stats_ws;   /* fp32 workspace [batch * groups * 2] */
+    int stats_prezeroed; /* 1: the caller guarantees stats_ws is zero on entry (e.g. one memset per step over an arena of
+                            workspaces): no memset node in front of the statistics kernel, which is then PDL-chained */
 } ctrlora_groupnorm_args;
 int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* args, void* stream);
 
