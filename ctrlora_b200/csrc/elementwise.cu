@@ -180,6 +180,34 @@ ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ e_cond
     }
 }
 
+// q_sample / stochastic_encode (ldm/models/diffusion/ddpm.py:356-359, cldm/ddim_hacked.py:281-296): integer gather of the two
+// per-timestep coefficients, then a*x0 + s*noise with separately rounded products (bit-identical to the reference's fp32
+// tensor expression).
+__global__ void __launch_bounds__(256)
+q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
+                const float* __restrict__ tab_a, const float* __restrict__ tab_s, float* __restrict__ out, int per_image,
+                int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long ti = t[i / per_image];
+    out[i] = __fadd_rn(__fmul_rn(tab_a[ti], x0[i]), __fmul_rn(tab_s[ti], noise[i]));
+}
+
+// DDIM inversion step (cldm/ddim_hacked.py:253-267): optional CFG combine, then x_next = c1*x + c2*e, products rounded
+// separately like the reference's tensor expression.
+__global__ void __launch_bounds__(256)
+ddim_encode_kernel(const float* __restrict__ x, const float* __restrict__ e_cond, const float* __restrict__ e_uncond,
+                   float* __restrict__ x_next, int total, float cfg_scale, float c1, float c2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float e = e_cond[i];
+    if (e_uncond) {
+        const float u = e_uncond[i];
+        e = __fadd_rn(u, __fmul_rn(cfg_scale, __fsub_rn(e, u)));
+    }
+    x_next[i] = __fadd_rn(__fmul_rn(c1, x[i]), __fmul_rn(c2, e));
+}
+
 static inline unsigned blocks_for(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace ctrl
@@ -353,5 +381,20 @@ extern "C" int ctrlora_ddim_update(const float* x, const float* e_cond, const fl
     ddim_update_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(
         x, e_cond, e_uncond, noise, x_prev, pred_x0, stats, per_image, total, cfg_scale, sqrt_a_t, sqrt_a_prev, dir_coef,
         sigma_t, temperature, sqrt_one_minus_at);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a,
+                                const float* tab_s, float* out, int batch, int per_image, void* stream) {
+    if (!x0 || !noise || !t || !tab_a || !tab_s || !out) return CTRLORA_ERR_ARG;
+    const int total = batch * per_image;
+    q_sample_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(x0, noise, t, tab_a, tab_s, out, per_image, total);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_ddim_encode_update(const float* x, const float* e_cond, const float* e_uncond, float* x_next,
+                                          int total, float cfg_scale, float c1, float c2, void* stream) {
+    if (!x || !e_cond || !x_next) return CTRLORA_ERR_ARG;
+    ddim_encode_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(x, e_cond, e_uncond, x_next, total, cfg_scale, c1, c2);
     return LAUNCH_OK();
 }

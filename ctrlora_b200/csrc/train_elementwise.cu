@@ -173,9 +173,10 @@ __global__ void mse_loss_grad_kernel(const float* __restrict__ eps, const float*
 // torch.optim.AdamW semantics (decoupled weight decay, bias correction), fp32 master params, one flat buffer.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-                             float grad_scale) {
+                             float grad_scale, const int* __restrict__ skip_flag) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (skip_flag && *skip_flag) return;  // a non-finite gradient was seen this step (loss-scale overflow): no update
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
@@ -185,6 +186,99 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
     pi -= (lr / bc1) * (mi / denom);
     p[i] = pi;
+}
+
+// flag |= any(!isfinite(x)): the overflow check of static/dynamic loss scaling (fp16 activation gradients)
+__global__ void nonfinite_flag_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+    bool bad = false;
+    for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n) {
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+        } else {
+            for (long long j = i; j < n; ++j) bad |= !isfinite(x[j]);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// out = sum_i w[i] * src[i]  (fp16 tensors of n elements, fp32 accumulate): the multi-LoRA control sum
+// (cldm/cldm_ctrlora_inference.py:172-176) in one pass
+struct WeightedSumArgs {
+    const __half* src[8];
+    float w[8];
+    int count;
+};
+__global__ void weighted_sum_kernel(const __grid_constant__ WeightedSumArgs a, __half* __restrict__ out, long long nvec) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < a.count; ++s) {
+        float t[8];
+        ld8(a.src[s] + i * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += a.w[s] * t[e];
+    }
+    st8(out + i * 8, acc);
+}
+
+// stride-1 3x3 pad-1 gather: col[b, h, w, tap, c] = x[b, h + kh - 1, w + kw - 1, c] (0 outside): the token-major operand
+// of the dense conv weight gradient dW[Cout, tap, Cin] = dY^T col (pretraining: every ControlNet conv is trainable)
+__global__ void im2col_3x3_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int vecs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * H * W * 9 * vecs;
+    if (i >= total) return;
+    const int v = static_cast<int>(i % vecs);
+    long long r = i / vecs;
+    const int tap = static_cast<int>(r % 9);
+    r /= 9;
+    const int w = static_cast<int>(r % W);
+    r /= W;
+    const int h = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = src[((static_cast<long long>(b) * H + ih) * W + iw) * vecs + v];
+    dst[i] = val;
+}
+
+// out[n, k] (+)= alpha * sum_b dy[b, n] * x[b, k]   (fp32, b = batch rows <= 64): weight gradients of the time-embedding
+// MLP / emb_layers linears, where the "token" dimension is just the batch
+__global__ void __launch_bounds__(256)
+outer_accum_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, float* __restrict__ out,
+                   long long ldo, int rows, int N, int K, float alpha, float beta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (k >= K) return;
+    float acc = 0.f;
+    for (int b = 0; b < rows; ++b) acc += dy[b * lddy + n] * x[b * ldx + k];
+    float* o = out + n * ldo + k;
+    *o = beta * (*o) + alpha * acc;
+}
+
+// out = d * silu'(x)  (fp32)
+__global__ void silu_bwd_kernel(const float* __restrict__ d, const float* __restrict__ x, float* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float z = x[i];
+    const float s = 1.0f / (1.0f + __expf(-z));
+    out[i] = d[i] * s * (1.0f + z * (1.0f - s));
+}
+
+// fp32 [rows, cols] with arbitrary row stride -> fp16 dense (weight copies of parameters stored in kernel layout)
+__global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst, long long rows, int cols) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    dst[i] = __float2half_rn(src[(i / cols) * lds + (i % cols)]);
 }
 
 static inline unsigned nblk(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
@@ -264,10 +358,63 @@ extern "C" int ctrlora_mse_loss_grad(const float* eps, const float* noise, float
 
 extern "C" int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                                 void* stream) {
+                                 const int* skip_flag, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) return CTRLORA_ERR_ARG;
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     adamw_kernel<<<nblk(n, 256), 256, 0, STREAM(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                           weight_decay, bc1, bc2, grad_scale);
+                                                           weight_decay, bc1, bc2, grad_scale, skip_flag);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_nonfinite_flag_f32(const float* x, long long n, int* flag, void* stream) {
+    if (!x || !flag || (reinterpret_cast<uintptr_t>(x) & 15)) return CTRLORA_ERR_ARG;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    nonfinite_flag_kernel<<<static_cast<unsigned>(blocks), 256, 0, STREAM(stream)>>>(x, n, flag);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_weighted_sum_f16(const void* const* srcs, const float* weights, int count, void* out, long long n,
+                                        void* stream) {
+    if (!srcs || !weights || !out || count < 1 || count > 8 || n % 8) return CTRLORA_ERR_ARG;
+    WeightedSumArgs a;
+    a.count = count;
+    for (int i = 0; i < count; ++i) {
+        if (!srcs[i] || (reinterpret_cast<uintptr_t>(srcs[i]) & 15)) return CTRLORA_ERR_ARG;
+        a.src[i] = reinterpret_cast<const __half*>(srcs[i]);
+        a.w[i] = weights[i];
+    }
+    launch_pdl(weighted_sum_kernel, dim3(nblk(n / 8, 256)), dim3(256), (size_t)0, STREAM(stream), a,
+               reinterpret_cast<__half*>(out), n / 8);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_im2col_3x3_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream) {
+    if (!src || !dst || channels % 8 != 0) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    const long long total = static_cast<long long>(batch) * h * w * 9 * vecs;
+    launch_pdl(im2col_3x3_kernel, dim3(nblk(total, 256)), dim3(256), (size_t)0, STREAM(stream),
+               reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), batch, h, w, vecs);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_outer_accum_f32(const float* dy, int lddy, const float* x, int ldx, float* out, long long ldo, int rows,
+                                       int n, int k, float alpha, float beta, void* stream) {
+    if (!dy || !x || !out || rows < 1 || n < 1 || k < 1) return CTRLORA_ERR_ARG;
+    launch_pdl(outer_accum_kernel, dim3((k + 255) / 256, n), dim3(256), (size_t)0, STREAM(stream), dy, lddy, x, ldx, out, ldo,
+               rows, n, k, alpha, beta);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_silu_bwd_f32(const float* d, const float* x, float* out, long long n, void* stream) {
+    if (!d || !x || !out) return CTRLORA_ERR_ARG;
+    launch_pdl(silu_bwd_kernel, dim3(nblk(n, 256)), dim3(256), (size_t)0, STREAM(stream), d, x, out, n);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_cast_rows_f32_to_f16(const float* src, long long lds, void* dst, long long rows, int cols, void* stream) {
+    if (!src || !dst) return CTRLORA_ERR_ARG;
+    cast_rows_kernel<<<nblk(rows * cols, 256), 256, 0, STREAM(stream)>>>(src, lds, reinterpret_cast<__half*>(dst), rows, cols);
     return LAUNCH_OK();
 }

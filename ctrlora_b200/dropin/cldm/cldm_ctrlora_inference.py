@@ -98,12 +98,8 @@ class ControlInferenceLDM(ControlLDM):
         if len(stacks) == 1:
             control = [Scaled(c, s * self.lora_weights[0]) for c, s in zip(stacks[0], self.control_scales)]
         else:
-            # sum_i w_i * scale_j * control_i[j]  (reference :172-176); tiny tensors, merged once per call
-            control = []
-            for j, s in enumerate(self.control_scales):
-                acc = stacks[0][j].float() * (s * self.lora_weights[0])
-                for i in range(1, len(stacks)):
-                    acc = acc + stacks[i][j].float() * (s * self.lora_weights[i])
-                control.append(acc.half().contiguous(memory_format=torch.channels_last))
+            # sum_i w_i * scale_j * control_i[j]  (reference :172-176): one n-ary kernel per residual, fp32 accumulate
+            control = [ops.weighted_sum([st[j] for st in stacks], [s * w for w in self.lora_weights])
+                       for j, s in enumerate(self.control_scales)]
         return diffusion_model(x=x_noisy, timesteps=t, context=cond_txt, control=control,
                                only_mid_control=self.only_mid_control)

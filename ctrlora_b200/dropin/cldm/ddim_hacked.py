@@ -27,6 +27,8 @@ class DDIMSampler(object):
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
+        self._fp_params = None
+        self._cfg_buf = None
         self.last_stats = None
 
     def register_buffer(self, name, attr):
@@ -160,6 +162,43 @@ class DDIMSampler(object):
                 i += n
         return out
 
+    def _weights_fingerprint(self):
+        """State of everything a captured apply_model graph bakes in besides shapes: the kernel-layout weight copies
+        (ctrlora_b200.prepare) are built during warm-up, outside the capture, so a `load_state_dict` /
+        `copy_weights_to_switchable` / optimizer step on the same model (the reference's gradio app re-uses one sampler
+        across checkpoints, app/gradio_ctrlora.py) must invalidate the graph.  torch bumps `_version` on every in-place
+        write; storage swaps change `data_ptr`; the trainer's fused AdamW bumps prepare.TRAIN_VERSION."""
+        from ctrlora_b200 import prepare
+        if self._fp_params is None:
+            self._fp_params = list(self.model.control_model.parameters()) + list(self.model.model.diffusion_model.parameters())
+        ver, ptr = 0, 0
+        for p in self._fp_params:
+            ver += p._version
+            ptr ^= p.data_ptr()
+        lw = getattr(self.model, "lora_weights", None)
+        return (ver, ptr, len(self._fp_params), prepare.TRAIN_VERSION, None if lw is None else tuple(float(w) for w in lw))
+
+    def _cfg_inputs(self, x, t, cond_tensors, uncond_tensors):
+        """[cond | uncond] batch of one CFG step in persistent buffers: plain device-to-device copies (no ATen cat
+        kernels per step); the conditioning halves are re-copied only when their tensors change."""
+        b = x.shape[0]
+        sig = (tuple(x.shape), x.dtype, tuple((tuple(a.shape), a.dtype) for a in cond_tensors))
+        if self._cfg_buf is None or self._cfg_buf["sig"] != sig:
+            mk = lambda a: torch.empty((2 * a.shape[0],) + tuple(a.shape[1:]), device=a.device, dtype=a.dtype)
+            self._cfg_buf = {"sig": sig, "x": mk(x), "t": mk(t), "c": [mk(a) for a in cond_tensors], "src": None}
+        buf = self._cfg_buf
+        buf["x"][:b].copy_(x, non_blocking=True)
+        buf["x"][b:].copy_(x, non_blocking=True)
+        buf["t"][:b].copy_(t, non_blocking=True)
+        buf["t"][b:].copy_(t, non_blocking=True)
+        src = tuple((a.data_ptr(), a._version, u.data_ptr(), u._version) for a, u in zip(cond_tensors, uncond_tensors))
+        if buf["src"] != src:
+            for dst, a, u in zip(buf["c"], cond_tensors, uncond_tensors):
+                dst[:b].copy_(a, non_blocking=True)
+                dst[b:].copy_(u, non_blocking=True)
+            buf["src"] = src
+        return buf["x"], buf["t"], buf["c"]
+
     def _eps_pair(self, x, t, c, uc, use_cfg):
         """(e_cond, e_uncond | None) with the policy chosen at construction (batched CFG, CUDA graph)."""
         if not use_cfg:
@@ -168,24 +207,24 @@ class DDIMSampler(object):
         if self.batched_cfg and fc is not None and fu is not None and fc[0] == fu[0] and \
                 all(a.shape == b_.shape for a, b_ in zip(fc[1], fu[1])):
             b = x.shape[0]
-            both = [torch.cat([a, b_], 0) for a, b_ in zip(fc[1], fu[1])]
-            e = self._apply(torch.cat([x, x], 0), torch.cat([t, t], 0), self._rebuild(fc[0], both))
+            x2, t2, both = self._cfg_inputs(x, t, fc[1], fu[1])
+            e = self._apply(x2, t2, self._rebuild(fc[0], both), persistent=True)
             return e[:b], e[b:]
         e_c = self._apply(x, t, c)
         if self.use_cuda_graph:
             e_c = e_c.clone()  # the graph's static output buffer is overwritten by the second replay
         return e_c, self._apply(x, t, uc)
 
-    def _apply(self, x, t, c):
+    def _apply(self, x, t, c, persistent=False):
         flat = self._flat_cond(c)
         if not self.use_cuda_graph or flat is None or not x.is_cuda:
             return self.model.apply_model(x, t, c)
         keys, tensors = flat
         key = (keys, tuple(x.shape), tuple(tuple(tt.shape) for tt in tensors), tuple(self.model.control_scales),
-               self.model.only_mid_control)
+               self.model.only_mid_control, self._weights_fingerprint())
         if self._graph is None or self._graph_key != key:
             fn = lambda xx, tt, *cs: self.model.apply_model(xx, tt, self._rebuild(keys, list(cs)))
-            self._graph = GraphedCallable(fn, [x, t] + tensors)
+            self._graph = GraphedCallable(fn, [x, t] + tensors, adopt_inputs=persistent)
             self._graph_key = key
         return self._graph(x, t, *tensors)
 
@@ -220,28 +259,31 @@ class DDIMSampler(object):
         return x_prev, pred_x0
 
     # ---------------------------------------------------------------------------------------------- encode / decode
+    def _tables(self, use_original_steps, device):
+        """(alpha table, sqrt(alpha), sqrt(1 - alpha)) as fp32 device tensors for either schedule."""
+        if use_original_steps:
+            return self.alphas_cumprod, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
+        a = torch.as_tensor(self.ddim_alphas, dtype=torch.float32).to(device)
+        return a, torch.sqrt(a), torch.as_tensor(self.ddim_sqrt_one_minus_alphas, dtype=torch.float32).to(device)
+
     @torch.no_grad()
     def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
-        if use_original_steps:
-            sqrt_ac, sqrt_1m = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
-        else:
-            sqrt_ac = torch.sqrt(self.ddim_alphas.to(x0.device))
-            sqrt_1m = torch.as_tensor(self.ddim_sqrt_one_minus_alphas).to(x0.device)
+        """x_t = sqrt(a_t) x0 + sqrt(1 - a_t) noise with t indexing the chosen schedule (reference :281-296): the same
+        gather-and-blend kernel as q_sample."""
+        _, sqrt_a, sqrt_1m = self._tables(use_original_steps, x0.device)
         if noise is None:
             noise = torch.randn_like(x0)
-        return extract_into_tensor(sqrt_ac, t, x0.shape) * x0 + extract_into_tensor(sqrt_1m, t, x0.shape) * noise
+        return ops.q_sample(x0, noise, t, sqrt_a, sqrt_1m)
 
     @torch.no_grad()
     def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
                use_original_steps=False, callback=None):
-        timesteps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
-        timesteps = timesteps[:t_start]
-        time_range = np.flip(timesteps)
-        total_steps = timesteps.shape[0]
+        """Run the last `t_start` sampler steps from x_latent (reference :298-317)."""
+        steps = (np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps)[:t_start]
         x_dec = x_latent
-        for i, step in enumerate(time_range):
-            index = total_steps - i - 1
-            ts = torch.full((x_latent.shape[0],), int(step), device=x_latent.device, dtype=torch.long)
+        ts = torch.empty((x_latent.shape[0],), device=x_latent.device, dtype=torch.long)
+        for i, index in enumerate(range(len(steps) - 1, -1, -1)):
+            ts.fill_(int(steps[index]))
             x_dec, _ = self.p_sample_ddim(x_dec, cond, ts, index=index, use_original_steps=use_original_steps,
                                           unconditional_guidance_scale=unconditional_guidance_scale,
                                           unconditional_conditioning=unconditional_conditioning)
@@ -252,35 +294,36 @@ class DDIMSampler(object):
     @torch.no_grad()
     def encode(self, x0, c, t_enc, use_original_steps=False, return_intermediates=None,
                unconditional_guidance_scale=1.0, unconditional_conditioning=None, callback=None):
-        """DDIM inversion (reference :233-279), eps from the same graph-replayed apply_model."""
-        timesteps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
-        num_reference_steps = timesteps.shape[0]
-        assert t_enc <= num_reference_steps
-        num_steps = t_enc
+        """DDIM inversion x_0 -> x_{t_enc} (reference :233-279).  Each step is eps (graph-replayed apply_model, batched
+        CFG like p_sample_ddim -- the reference's own CFG branch concatenates the cond dicts and cannot run with a
+        ControlLDM) followed by ONE update kernel; the two per-step coefficients are evaluated on the host in fp32 with
+        the reference's operation order, so scale-1 results are bit-identical given the same eps."""
+        steps = np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps
+        assert t_enc <= steps.shape[0]
         if use_original_steps:
-            alphas_next = self.alphas_cumprod[:num_steps]
-            alphas = self.alphas_cumprod_prev[:num_steps]
+            a_next_tab, a_tab = self.alphas_cumprod[:t_enc].cpu(), self.alphas_cumprod_prev[:t_enc].cpu()
         else:
-            alphas_next = self.ddim_alphas[:num_steps].to(x0.device)
-            alphas = torch.tensor(self.ddim_alphas_prev[:num_steps], device=x0.device)
-        x_next, intermediates, inter_steps = x0, [], []
-        for i in range(num_steps):
-            t = torch.full((x0.shape[0],), int(timesteps[i]), device=x0.device, dtype=torch.long)
-            use_cfg = not (unconditional_guidance_scale == 1. or unconditional_conditioning is None)
+            a_next_tab = torch.as_tensor(self.ddim_alphas[:t_enc], dtype=torch.float32).cpu()
+            a_tab = torch.tensor(self.ddim_alphas_prev[:t_enc])  # numpy float64 holding fp32 values, like the reference:
+            # the per-step coefficients below are then evaluated in float64 and rounded to fp32 once, as torch does when a
+            # 0-dim float64 tensor multiplies an fp32 tensor
+        use_cfg = not (unconditional_guidance_scale == 1. or unconditional_conditioning is None)
+        x_next, kept, kept_steps = x0, [], []
+        t = torch.empty((x0.shape[0],), device=x0.device, dtype=torch.long)
+        every = (t_enc // return_intermediates) if return_intermediates else 0
+        for i in range(t_enc):
+            t.fill_(int(steps[i]))
             e_c, e_u = self._eps_pair(x_next, t, c, unconditional_conditioning, use_cfg)
-            noise_pred = e_c if e_u is None else e_u + unconditional_guidance_scale * (e_c - e_u)
-            xt_weighted = (alphas_next[i] / alphas[i]).sqrt() * x_next
-            weighted_noise_pred = alphas_next[i].sqrt() * ((1 / alphas_next[i] - 1).sqrt() - (1 / alphas[i] - 1).sqrt()) * noise_pred
-            x_next = xt_weighted + weighted_noise_pred
-            if return_intermediates and i % (num_steps // return_intermediates) == 0 and i < num_steps - 1:
-                intermediates.append(x_next)
-                inter_steps.append(i)
-            elif return_intermediates and i >= num_steps - 2:
-                intermediates.append(x_next)
-                inter_steps.append(i)
+            an, a = a_next_tab[i], a_tab[i]
+            c1 = (an / a).sqrt()
+            c2 = an.sqrt() * ((1 / an - 1).sqrt() - (1 / a - 1).sqrt())
+            x_next = ops.ddim_encode_update(x_next, e_c, e_u, unconditional_guidance_scale, float(c1), float(c2))
+            if return_intermediates and ((i % every == 0 and i < t_enc - 1) or i >= t_enc - 2):
+                kept.append(x_next)
+                kept_steps.append(i)
             if callback:
                 callback(i)
-        out = {'x_encoded': x_next, 'intermediate_steps': inter_steps}
+        out = {'x_encoded': x_next, 'intermediate_steps': kept_steps}
         if return_intermediates:
-            out.update({'intermediates': intermediates})
+            out['intermediates'] = kept
         return x_next, out

@@ -99,6 +99,10 @@ class DDPM(nn.Module):
 
     def q_sample(self, x_start, t, noise=None):
         noise = default(noise, lambda: torch.randn_like(x_start))
+        if x_start.is_cuda and x_start.dtype == torch.float32:
+            from ctrlora_b200 import ops
+            return ops.q_sample(x_start, noise, t, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod)
+        # host-side tensors (schedule checks on CPU): the reference's own expression
         return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
                 extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
 

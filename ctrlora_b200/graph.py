@@ -13,9 +13,11 @@ class GraphedCallable:
     Inputs are copied into static buffers before each replay; outputs are static buffers (clone them if they must
     survive the next call)."""
 
-    def __init__(self, fn, example_inputs, warmup=2):
+    def __init__(self, fn, example_inputs, warmup=2, adopt_inputs=False):
         self.fn = fn
-        self.static_in = [t.clone() if torch.is_tensor(t) else t for t in example_inputs]
+        # adopt_inputs: the caller's tensors ARE the static buffers (it keeps them alive and refills them in place), so a
+        # call with the same tensors copies nothing
+        self.static_in = [(t if adopt_inputs else t.clone()) if torch.is_tensor(t) else t for t in example_inputs]
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)

@@ -99,7 +99,7 @@ def replay_gemms(fn, sampler=None, reps=5):
 
 
 _SPLITK = {}  # device index -> (fp32 workspace, uint32 counters); zero on entry and on exit of every GEMM launch
-SPLITK_WS_BYTES = 48 << 20
+SPLITK_WS_BYTES = 128 << 20  # one fp32 [1280, 9*1280] dense-conv gradient slice is 59 MB
 SPLITK_COUNTERS = 4096
 
 
@@ -436,6 +436,74 @@ def ddim_update(x, e_cond, e_uncond, cfg_scale, a_t, a_prev, sigma_t, sqrt_one_m
     return x_prev, pred_x0
 
 
+def im2col_3x3(x):
+    """fp16 [B,H,W,C] -> [B,H,W,9*C] (stride 1, pad 1; tap-major like the conv kernel weights)"""
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float16
+    b, h, w, c = x.shape
+    y = torch.empty((b, h, w, 9 * c), device=x.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_im2col_3x3_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "im2col_3x3")
+    return y
+
+
+def outer_accum(dy, x, out, alpha=1.0, beta=1.0):
+    """out[n, k] = beta*out + alpha * sum_b dy[b, n] x[b, k]  (fp32 [B,N], [B,K] -> fp32 [N,K], row strides free)"""
+    _require_cuda(dy, x, out)
+    assert dy.dtype == x.dtype == out.dtype == torch.float32 and dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1
+    rows, n = dy.shape
+    k = x.shape[1]
+    assert x.shape[0] == rows and out.shape == (n, k)
+    _count()
+    check(_lib.load().ctrlora_outer_accum_f32(_dp(dy), dy.stride(0), _dp(x), x.stride(0), _dp(out), out.stride(0), rows, n, k,
+                                              float(alpha), float(beta), _sp()), "outer_accum")
+    return out
+
+
+def silu_bwd(d, x):
+    """d * silu'(x), fp32"""
+    _require_cuda(d, x)
+    d, x = d.contiguous(), x.contiguous()
+    out = torch.empty_like(d)
+    _count()
+    check(_lib.load().ctrlora_silu_bwd_f32(_dp(d), _dp(x), _dp(out), d.numel(), _sp()), "silu_bwd")
+    return out
+
+
+def cast_rows(src, rows, cols, lds):
+    """fp32 [rows, cols] with row stride lds -> dense fp16 [rows, cols]"""
+    _require_cuda(src)
+    out = torch.empty((rows, cols), device=src.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_cast_rows_f32_to_f16(_dp(src), lds, _dp(out), rows, cols, _sp()), "cast_rows")
+    return out
+
+
+def q_sample(x0, noise, t, tab_a, tab_s):
+    """tab_a[t] * x0 + tab_s[t] * noise (fp32 [B,...] contiguous; t int64 [B]; tables fp32 on the device). Bit-exact."""
+    _require_cuda(x0, noise, t, tab_a, tab_s)
+    x0, noise = x0.float().contiguous(), noise.float().contiguous()
+    assert t.dtype == torch.int64 and tab_a.dtype == torch.float32 and tab_s.dtype == torch.float32
+    assert x0.shape == noise.shape and t.numel() == x0.shape[0]
+    out = torch.empty_like(x0)
+    _count()
+    check(_lib.load().ctrlora_q_sample(_dp(x0), _dp(noise), _dp(t.contiguous()), _dp(tab_a.contiguous()),
+                                       _dp(tab_s.contiguous()), _dp(out), x0.shape[0], x0[0].numel(), _sp()), "q_sample")
+    return out
+
+
+def ddim_encode_update(x, e_cond, e_uncond, cfg_scale, c1, c2):
+    """x_next = c1 * x + c2 * cfg(e_cond, e_uncond)   (DDIM inversion, cldm/ddim_hacked.py:253-267)"""
+    _require_cuda(x, e_cond, e_uncond)
+    x, e_cond = x.float().contiguous(), e_cond.float().contiguous()
+    e_uncond = None if e_uncond is None else e_uncond.float().contiguous()
+    out = torch.empty_like(x)
+    _count()
+    check(_lib.load().ctrlora_ddim_encode_update(_dp(x), _dp(e_cond), _dp(e_uncond), _dp(out), x.numel(), float(cfg_scale),
+                                                 float(c1), float(c2), _sp()), "ddim_encode_update")
+    return out
+
+
 def wgrad_tn(a, b, out=None, alpha=1.0, beta=0.0):
     """out[p, q] = alpha * sum_m a[m, p] * b[m, q] + beta * out  (fp16 a [M,P], b [M,Q] -> fp32 [P,Q])."""
     _require_cuda(a, b)
@@ -572,13 +640,43 @@ def mse_loss_grad(eps, noise, c_pad=8, grad_scale=1.0):
 
 
 def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-               grad_scale=1.0):
-    """In-place AdamW over flat fp32 buffers (torch.optim.AdamW semantics)."""
+               grad_scale=1.0, skip_flag=None):
+    """In-place AdamW over flat fp32 buffers (torch.optim.AdamW semantics).  skip_flag: device int32 [1]; non-zero =
+    the step is skipped (non-finite gradients under loss scaling)."""
     _require_cuda(params, grads)
     _count()
     check(_lib.load().ctrlora_adamw_f32(_dp(params), _dp(grads), _dp(exp_avg), _dp(exp_avg_sq), params.numel(), float(lr),
                                         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
-                                        float(grad_scale), _sp()), "adamw")
+                                        float(grad_scale), _dp(skip_flag), _sp()), "adamw")
+
+
+def nonfinite_flag(x, flag):
+    """flag (int32 [1], device) |= any(!isfinite(x)); x fp32 flat."""
+    _require_cuda(x, flag)
+    assert x.dtype == torch.float32 and x.is_contiguous() and flag.dtype == torch.int32
+    _count()
+    check(_lib.load().ctrlora_nonfinite_flag_f32(_dp(x), x.numel(), _dp(flag), _sp()), "nonfinite_flag")
+    return flag
+
+
+def weighted_sum(tensors, weights, out=None):
+    """sum_i weights[i] * tensors[i] over up to 8 same-shape, same-stride dense fp16 tensors (fp32 accumulate)."""
+    _require_cuda(*tensors)
+    t0 = tensors[0]
+    n = len(tensors)
+    assert 1 <= n <= 8 and len(weights) == n
+    for t in tensors:
+        assert t.dtype == torch.float16 and t.shape == t0.shape and t.stride() == t0.stride()
+    dense = t0.is_contiguous() or t0.is_contiguous(memory_format=torch.channels_last)
+    assert dense and t0.numel() % 8 == 0, "weighted_sum needs dense tensors with numel % 8 == 0"
+    if out is None:
+        out = torch.empty_like(t0)  # preserves the (dense) strides
+    assert out.stride() == t0.stride()
+    srcs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    ws = (C.c_float * n)(*[float(w) for w in weights])
+    _count()
+    check(_lib.load().ctrlora_weighted_sum_f16(srcs, ws, n, _dp(out), t0.numel(), _sp()), "weighted_sum")
+    return out
 
 
 def attention_bwd(q, k, v, o, dout, lse, batch, heads, nq, nk, head_dim, dq=None, dk=None, dv=None):

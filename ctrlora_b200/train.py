@@ -30,6 +30,11 @@ class GradSink:
 
     def __init__(self, control_model):
         from cldm.cldm_ctrlora_finetune import trainable_parameters
+        if not getattr(control_model, "ft_with_lora", True):
+            # full-ControlNet finetuning selects every parameter (cldm_ctrlora_finetune.py:101-104); this sink's backward
+            # only produces LoRA / zero-conv / norm gradients -- stepping the rest would be pure weight decay
+            raise NotImplementedError("FinetuneTrainer covers ft_with_lora=True; use PretrainTrainer (dense weight "
+                                      "gradients of every ControlNet parameter) for full-parameter training")
         named = trainable_parameters(control_model)
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
@@ -526,7 +531,8 @@ def unet_bwd(unet, saved, d_eps16):
 class FinetuneTrainer:
     """One data-parallel CtrLoRA finetune step per call (configs ctrlora_finetune_sd15_rank*.yaml)."""
 
-    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None):
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None,
+                 loss_scale=None, dynamic_loss_scale=True):
         self.model = model
         self.cn = model.control_model
         self.unet = model.model.diffusion_model
@@ -536,24 +542,52 @@ class FinetuneTrainer:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        if self.world > 1:
+            # DDP's construction-time rank-0 broadcast (the reference relies on it: LoRA `down` is initialised
+            # N(0, 1/r) without a seed, cldm/lora.py:67): every replica starts from rank 0's trainable parameters
+            torch.distributed.broadcast(self.G.flat_p, src=0, group=process_group)
+            prepare.bump_train_version()
         self.step_count = 0
+        # Loss scaling (the backward's activation gradients are fp16; the reference trains in fp32 and needs none):
+        # d(loss)/d(eps) = 2 (eps - noise) / numel is ~1e-5 at batch 16 x 4 x 64 x 64 -- below fp16's normal range.  The
+        # default scale makes it (eps - noise) / LOSS_SCALE_DIV independent of the batch shape; the AdamW kernel divides
+        # it out of the fp32 gradient buffer.  `dynamic`: a non-finite gradient skips the update and halves the scale.
+        self.loss_scale = loss_scale
+        self.dynamic_loss_scale = dynamic_loss_scale
+        self.overflow_flag = torch.zeros(1, device=self.G.flat_p.device, dtype=torch.int32)
+        self.skipped_steps = 0
+
+    LOSS_SCALE_DIV = 8.0
+    CHECK_OVERFLOW_EVERY = 1
+
+    def _scale_for(self, numel):
+        return float(self.loss_scale) if self.loss_scale is not None else numel / (2.0 * self.LOSS_SCALE_DIV)
 
     def loss_and_grads(self, x0, hint_latent, context, t, noise):
         """q_sample -> apply_model -> MSE -> backward into the flat gradient buffer.  Returns the loss (fp32 tensor)."""
         m = self.model
         self.G.zero()
+        self.overflow_flag.zero_()
+        self._scale_used = self._scale_for(x0.numel())
         ops.stats_arena_begin(x0.device)  # one memset for all GroupNorm forward / backward statistics of the step
-        x_noisy = m.q_sample(x_start=x0, t=t, noise=noise)
-        control, cn_saved = controlnet_fwd(self.cn, hint_latent, t, context)
-        eps, un_saved = unet_fwd(self.unet, x_noisy, t, context, control, m.control_scales, m.only_mid_control)
-        loss, d_eps = ops.mse_loss_grad(eps, noise, c_pad=un_saved["n_pad"])
-        d_ctrl = unet_bwd(self.unet, un_saved, d_eps)
-        if m.only_mid_control:
-            d_ctrl = [d if d is not None else torch.zeros_like(c) for d, c in zip(d_ctrl, control)]
-        controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G)
-        ops.stats_arena_end(x0.device)
+        try:
+            x_noisy = m.q_sample(x_start=x0, t=t, noise=noise)
+            control, cn_saved = controlnet_fwd(self.cn, hint_latent, t, context)
+            eps, un_saved = unet_fwd(self.unet, x_noisy, t, context, control, m.control_scales, m.only_mid_control)
+            loss, d_eps = ops.mse_loss_grad(eps, noise, c_pad=un_saved["n_pad"], grad_scale=self._scale_used)
+            d_ctrl = unet_bwd(self.unet, un_saved, d_eps)
+            if m.only_mid_control:
+                d_ctrl = [d if d is not None else torch.zeros_like(c) for d, c in zip(d_ctrl, control)]
+            controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G)
+        finally:
+            ops.stats_arena_end(x0.device)
         self.last_eps = eps
         return loss
+
+    def unscaled_grads(self):
+        """{name: fp32 gradient} with the loss scale divided out (what the reference's autograd would hold)."""
+        inv = 1.0 / self._scale_used
+        return {n: g * inv for n, g in self.G.named_grads().items()}
 
     def reduce_gradients(self):
         """The path's single exchange step: ONE all-reduce (SUM) of the flat trainable-gradient buffer (36.9 M fp32
@@ -594,8 +628,21 @@ class FinetuneTrainer:
         else:
             loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
         self.reduce_gradients()
+        ops.nonfinite_flag(self.G.flat_g, self.overflow_flag)  # after the all-reduce: every rank takes the same decision
         self.step_count += 1
         ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,
-                       betas=self.betas, eps=self.eps, weight_decay=self.wd, grad_scale=1.0 / self.world)
+                       betas=self.betas, eps=self.eps, weight_decay=self.wd,
+                       grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag)
         prepare.bump_train_version()
+        if self.dynamic_loss_scale and self.step_count % self.CHECK_OVERFLOW_EVERY == 0 and self._overflowed():
+            # GradScaler semantics: the update was skipped on the device; halve the scale (re-capturing the graph, whose
+            # loss kernel has the scale baked in) and do not count the step
+            self.step_count -= 1
+            self.skipped_steps += 1
+            self.loss_scale = self._scale_used * 0.5
+            if getattr(self, "_graph", None) is not None:
+                self.capture(*self._static, warmup=1)
         return loss
+
+    def _overflowed(self):
+        return bool(self.overflow_flag.item())

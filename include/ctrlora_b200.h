@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define CTRLORA_ABI_VERSION 1
+#define CTRLORA_ABI_VERSION 2
 
 /* status codes */
 #define CTRLORA_STATUS_OK 0
@@ -145,6 +145,16 @@ int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_unco
                         float* pred_x0, float* stats, int batch, int per_image, float cfg_scale, float a_t, float a_prev,
                         float sigma_t, float sqrt_one_minus_at, float temperature, void* stream);
 
+/* q_sample (ldm/models/diffusion/ddpm.py:356-359) and DDIMSampler.stochastic_encode (cldm/ddim_hacked.py:281-296):
+ * out[b] = tab_a[t[b]] * x0[b] + tab_s[t[b]] * noise[b]; t int64 [batch] (device), tables fp32 (device).  Bit-exact. */
+int ctrlora_q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_s,
+                     float* out, int batch, int per_image, void* stream);
+/* DDIM inversion step (cldm/ddim_hacked.py:253-267): e = e_uncond + cfg*(e_cond - e_uncond) (e_uncond may be NULL), then
+ * x_next = c1 * x + c2 * e with c1 = sqrt(a_next/a), c2 = sqrt(a_next) * (sqrt(1/a_next - 1) - sqrt(1/a - 1)) evaluated
+ * by the caller in fp32 like the reference's 0-dim tensor arithmetic. */
+int ctrlora_ddim_encode_update(const float* x, const float* e_cond, const float* e_uncond, float* x_next, int total,
+                               float cfg_scale, float c1, float c2, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Training (backward of the trainable set; reference: autograd over cldm/lora.py:70-80,285-291 and cldm/cldm.py:281-282,
  * parameters selected by cldm/cldm_ctrlora_finetune.py:88-100).
@@ -182,6 +192,17 @@ int ctrlora_geglu_bwd_f16(const void* h, const void* dout, void* dh, long long r
 int ctrlora_colsum(const void* x, int x_is_f32, long long ld, long long rows, int cols, float scale, float* out, void* stream);
 int ctrlora_image_colsum_f16(const void* x, long long ld, int images, int rows_per_img, int cols, float* out, long long ldo,
                              void* stream);
+/* Pretraining (every ControlNet parameter trainable, cldm/cldm_ctrlora_pretrain.py:174-182): dense weight gradients.
+ * dW[Cout, tap, Cin] of a 3x3 stride-1 conv = ctrlora_wgrad_tn_f16(dY [M, Cout], col [M, 9*Cin]) with
+ * col[b, h, w, tap, c] = x[b, h+kh-1, w+kw-1, c]: */
+int ctrlora_im2col_3x3_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
+/* out[n, k] = beta*out + alpha * sum_b dy[b, n] * x[b, k] (fp32; b = batch rows): time_embed / emb_layers weight gradients */
+int ctrlora_outer_accum_f32(const float* dy, int lddy, const float* x, int ldx, float* out, long long ldo, int rows, int n, int k,
+                            float alpha, float beta, void* stream);
+/* out = d * silu'(x) (fp32): backward of the SiLU in the time-embedding MLP (openaimodel.py:526-531, :208-215) */
+int ctrlora_silu_bwd_f32(const float* d, const float* x, float* out, long long n, void* stream);
+/* fp32 [rows, cols] (row stride lds) -> dense fp16 [rows, cols] */
+int ctrlora_cast_rows_f32_to_f16(const float* src, long long lds, void* dst, long long rows, int cols, void* stream);
 /* adjoints of ctrlora_upsample2x_f16 and ctrlora_im2col_s2_f16 */
 int ctrlora_upsample2x_bwd_f16(const void* dout, void* din, int batch, int h, int w, int channels, void* stream);
 int ctrlora_im2col_s2_bwd_f16(const void* dcol, void* dx, int batch, int h, int w, int channels, void* stream);
@@ -190,9 +211,17 @@ int ctrlora_im2col_s2_bwd_f16(const void* dcol, void* dx, int batch, int h, int 
 int ctrlora_mse_loss_grad(const float* eps, const float* noise, float* loss, void* grad, int batch, int channels, int hw,
                           int c_pad, float grad_scale, void* stream);
 /* torch.optim.AdamW step over one flat fp32 buffer (cldm/cldm_ctrlora_finetune.py:105: lr 1e-5, betas .9/.999, eps 1e-8,
- * weight decay 0.01); grads are multiplied by grad_scale first (1/world_size after an all-reduce SUM). */
+ * weight decay 0.01); grads are multiplied by grad_scale first (1/(world_size * loss_scale) after an all-reduce SUM).
+ * skip_flag (device int, may be NULL): when non-zero the step is skipped (loss-scale overflow, see below). */
 int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+                      float beta2, float eps, float weight_decay, int step, float grad_scale, const int* skip_flag,
+                      void* stream);
+/* *flag |= 1 if any element of x is NaN/Inf: the overflow check of the loss-scaled fp16 backward (the reference trains in
+ * fp32 and has no such step; torch.cuda.amp.GradScaler semantics: skip the update, lower the scale). */
+int ctrlora_nonfinite_flag_f32(const float* x, long long n, int* flag, void* stream);
+/* out = sum_i weights[i] * srcs[i] over `count` (<= 8) fp16 tensors of n elements (n % 8 == 0), fp32 accumulation:
+ * the weighted control sum of multi-LoRA inference, cldm/cldm_ctrlora_inference.py:172-176.  srcs / weights: HOST arrays. */
+int ctrlora_weighted_sum_f16(const void* const* srcs, const float* weights, int count, void* out, long long n, void* stream);
 
 #ifdef __cplusplus
 }

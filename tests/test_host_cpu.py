@@ -35,7 +35,7 @@ def test_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ctrlora_abi_version() == 1
+    assert lib.ctrlora_abi_version() == 2
 
 
 def test_gemm_args_struct_layout_matches_header():

@@ -5,18 +5,19 @@ DDIM update and the integer/index-driven kernels (layout conversion, upsample, s
 """
 import math
 
+import os
+import sys
+
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
 
-def _close(got, ref, tol=2e-3):
-    got, ref = got.float(), ref.float()
-    err = (got - ref).abs().max().item()
-    scale = ref.abs().max().item() + 1e-6
-    assert err <= tol * scale, f"max err {err:.4e} vs scale {scale:.4e}"
+from tolerances import close as _close  # noqa: E402  (max-abs guard AND norm-relative <= 1e-3)
 
 
 def _rand(*shape, s=1.0, dtype=torch.float16):

@@ -181,9 +181,195 @@ def full(seed=0):
     print("wrote", out, os.path.getsize(out) // 1024, "KiB", "in", time.time() - t0, "s")
 
 
+def _variant_yaml(kind):
+    """tiny_finetune.yaml re-targeted at the pretrain / inference classes (same topology and widths)."""
+    txt = open(os.path.join(GOLD, "tiny_finetune.yaml")).read()
+    if kind == "pretrain":
+        txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlFinetuneLDM", "cldm.cldm_ctrlora_pretrain.ControlPretrainLDM")
+        txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlNetFinetune", "cldm.cldm_ctrlora_pretrain.ControlNetPretrain")
+        txt = txt.replace("        ft_with_lora: True\n        lora_rank: 8\n        norm_trainable: True\n",
+                          "        lora_rank: 8\n        tasks: [ canny, depth, seg ]\n")
+    else:
+        txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlFinetuneLDM", "cldm.cldm_ctrlora_inference.ControlInferenceLDM")
+        txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlNetFinetune", "cldm.cldm_ctrlora_inference.ControlNetInference")
+        txt = txt.replace("        ft_with_lora: True\n        lora_rank: 8\n        norm_trainable: True\n",
+                          "        lora_rank: 8\n        lora_num: 2\n")
+    assert "ft_with_lora" not in txt
+    out = os.path.join(GOLD, f"tiny_{kind}.yaml")
+    with open(out, "w") as f:
+        f.write(txt)
+    return out
+
+
+def variants(seed=0):
+    """Reference outputs of the pretrain / inference LDMs (tiny config): ControlPretrainLDM.apply_model per task,
+    ControlInferenceLDM.apply_model with 2 LoRA sets + weights, the pretrain training step (loss, gradient norms of ALL
+    control_model parameters = the pretrain optimizer's set, cldm_ctrlora_pretrain.py:174-182), and the sampler's
+    encode / decode / stochastic_encode."""
+    B, H = 2, 16
+    x = synth.synth_input("x", (B, 4, H, H), seed)
+    hint = synth.synth_input("hint", (B, 4, H, H), seed)
+    hint2 = synth.synth_input("hint2", (B, 4, H, H), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 64), seed)
+    uc_ctx = synth.synth_input("uc_ctx", (B, 77, 64), seed)
+    noise = synth.synth_input("noise", (B, 4, H, H), seed)
+    t = torch.tensor([981, 21], dtype=torch.long)
+    g = {"seed": seed, "B": B, "H": H, "t": t}
+
+    # ---------------- pretrain
+    model = build_reference(_variant_yaml("pretrain"), seed)
+    model.encode_first_stage = lambda h: h
+    model.get_first_stage_encoding = lambda h: h
+    cn = model.control_model
+    g["pretrain_control_shapes"], g["unet_shapes"] = shapes_of(cn), shapes_of(model.model.diffusion_model)
+    g["pretrain_key_order"] = list(cn.state_dict().keys())
+    with torch.no_grad():
+        for task in ("canny", "depth", "seg"):
+            g[f"pretrain_eps_{task}"] = model.apply_model(x, t, {"c_crossattn": [ctx], "c_concat": [hint], "task": task})
+        g["pretrain_eps_nocontrol"] = model.apply_model(x, t, {"c_crossattn": [ctx], "c_concat": None, "task": "canny"})
+    # training step on task 'depth' (p_losses arithmetic: ddpm.py:885-920)
+    x_noisy = model.q_sample(x_start=x, t=t, noise=noise)
+    for p in model.parameters():
+        p.grad = None
+    eps = model.apply_model(x_noisy, t, {"c_crossattn": [ctx], "c_concat": [hint], "task": "depth"})
+    loss = model.get_loss(eps, noise, mean=False).mean([1, 2, 3]).mean()
+    loss.backward()
+    g["pretrain_loss"] = loss.detach().clone()
+    g["pretrain_train_eps"] = eps.detach().clone()
+    named = list(cn.named_parameters())
+    g["pretrain_param_names"] = [n for n, _ in named]
+    g["pretrain_grad_norms"] = {n: (p.grad.norm().item() if p.grad is not None else None) for n, p in named}
+    keep = ("input_blocks.0.0.weight", "input_blocks.0.0.bias", "input_blocks.1.0.in_layers.2.weight",
+            "input_blocks.1.0.out_layers.3.weight", "input_blocks.1.0.emb_layers.1.weight", "input_blocks.3.0.op.weight",
+            "input_blocks.4.0.skip_connection.weight", "input_blocks.4.1.proj_in.weight",
+            "input_blocks.4.1.transformer_blocks.0.attn1.to_q.weight", "input_blocks.4.1.transformer_blocks.0.attn2.to_k.weight",
+            "input_blocks.4.1.transformer_blocks.0.ff.net.0.proj.weight", "input_blocks.4.1.transformer_blocks.0.ff.net.0.proj.bias",
+            "input_blocks.4.1.transformer_blocks.0.ff.net.2.weight", "middle_block.0.in_layers.0.weight",
+            "middle_block.1.proj_out.weight", "middle_block.2.out_layers.3.bias", "time_embed.0.weight", "time_embed.2.bias",
+            "zero_convs.3.0.weight", "middle_block_out.0.bias",
+            # the attached task's LoRA layers are reached (and de-duplicated by named_parameters) under `lora_layer`
+            "time_embed.0.lora_layer.down.weight", "time_embed.0.lora_layer.up.weight",
+            "input_blocks.4.1.transformer_blocks.0.attn1.to_q.lora_layer.down.weight",
+            "input_blocks.4.1.transformer_blocks.0.ff.net.2.lora_layer.up.weight")
+    grads = dict(named)
+    g["pretrain_grads"] = {n: grads[n].grad.clone() for n in keep}
+
+    # ---------------- inference (2 LoRA sets, weights 0.7 / 0.3, control_scales ramp)
+    model = build_reference(_variant_yaml("inference"), seed)
+    model.encode_first_stage = lambda h: h
+    model.get_first_stage_encoding = lambda h: h
+    cn = model.control_model
+    g["inference_control_shapes"] = shapes_of(cn)
+    g["inference_key_order"] = list(cn.state_dict().keys())
+    conds = [{"c_crossattn": [ctx], "c_concat": [hint]}, {"c_crossattn": [ctx], "c_concat": [hint2]}]
+    with torch.no_grad():
+        g["inference_eps_default"] = model.apply_model(x, t, conds)          # lora_weights = [0.5, 0.5]
+        model.lora_weights = [0.7, 0.3]
+        model.control_scales = [0.5 + 0.1 * i for i in range(13)]
+        g["inference_eps_weighted"] = model.apply_model(x, t, conds)
+        model.control_scales = [1.0] * 13
+        for i in (0, 1):
+            cn.switch_lora(i)
+            g[f"inference_control_{i}"] = [c.clone() for c in cn(hint=hint, timesteps=t, context=ctx)]
+
+    # ---------------- sampler encode / decode / stochastic_encode on the finetune model
+    model = build_reference(os.path.join(GOLD, "tiny_finetune.yaml"), seed)
+    model.encode_first_stage = lambda h: h
+    model.get_first_stage_encoding = lambda h: h
+    from cldm.ddim_hacked import DDIMSampler
+    sampler = DDIMSampler(model)
+    sampler.register_buffer = lambda name, attr: setattr(sampler, name, attr)
+    sampler.make_schedule(10, ddim_eta=0.0, verbose=False)
+    cond = {"c_crossattn": [ctx], "c_concat": [hint]}
+    ucond = {"c_crossattn": [uc_ctx], "c_concat": [hint]}
+    with torch.no_grad():
+        # scale 1: the reference's CFG branch of encode() concatenates the cond dicts (:258-260) and cannot run here
+        x_enc, out = sampler.encode(x, cond, 4, return_intermediates=2)
+        g["encode"] = {"x_encoded": x_enc, "intermediate_steps": out["intermediate_steps"],
+                       "n_intermediates": len(out["intermediates"])}
+        g["decode"] = sampler.decode(x, cond, 4, unconditional_guidance_scale=3.0, unconditional_conditioning=ucond)
+        tt = torch.tensor([3, 7], dtype=torch.long)
+        # use_original_steps: the DDIM-table branch gathers from a numpy array in the reference (:289) and raises
+        g["stochastic_encode"] = {"t": tt, "out": sampler.stochastic_encode(x, tt, use_original_steps=True, noise=noise)}
+    # finetune training step with only_mid_control=True (cldm/cldm.py:39-42: the 12 skip residuals are unused)
+    model.only_mid_control = True
+    x_noisy = model.q_sample(x_start=x, t=t, noise=noise)
+    for p in model.parameters():
+        p.grad = None
+    eps = model.apply_model(x_noisy, t, cond)
+    loss = model.get_loss(eps, noise, mean=False).mean([1, 2, 3]).mean()
+    loss.backward()
+    names = [n for n, _ in model.control_model.named_parameters()
+             if "lora_layer" in n or "zero_convs" in n or "middle_block_out" in n or "norm" in n]
+    gr = dict(model.control_model.named_parameters())
+    g["midonly_train"] = {"loss": loss.detach().clone(), "eps": eps.detach().clone(),
+                          "grad_norms": {n: (gr[n].grad.norm().item() if gr[n].grad is not None else 0.0) for n in names}}
+    out = os.path.join(GOLD, "tiny_variants_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
+def full_train(seed=0):
+    """SD1.5-size training step on the reference (rank-128 finetune config, B = 2, checkpointed autograd): loss and the
+    gradient norms of the optimizer's 246 tensors (cldm_ctrlora_finetune.py:88-100) + a few full tensors."""
+    t0 = time.time()
+    yaml_path = os.path.join(ref_shims.REFERENCE_ROOT, "configs", "ctrlora_finetune_sd15_rank128.yaml")
+    ref_shims.install()
+    from omegaconf import OmegaConf
+    from ldm.util import instantiate_from_config
+    from oracle import ctrlora_oracle as O
+    cfg = OmegaConf.load(yaml_path).model.params
+    with torch.device("meta"):
+        cn = instantiate_from_config(cfg.control_stage_config)
+        unet = instantiate_from_config(cfg.unet_config)
+    for sub, prefix in ((cn, "control_model."), (unet, "model.diffusion_model.")):
+        shapes = {k: tuple(v.shape) for k, v in sub.state_dict().items()}
+        sub.to_empty(device="cpu")
+        sub.load_state_dict(synth.synth_state_dict(shapes, seed, prefix), strict=True)
+    cn.train(), unet.train()   # checkpoint() only recomputes when parameters require grad; dropout is 0
+    print("built in", time.time() - t0, flush=True)
+    B = 2
+    x0 = synth.synth_input("x", (B, 4, 64, 64), seed)
+    hint = synth.synth_input("hint", (B, 4, 64, 64), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 768), seed)
+    noise = synth.synth_input("noise", (B, 4, 64, 64), seed)
+    t = torch.tensor([801, 131], dtype=torch.long)
+    sched = O.register_schedule()
+    x_noisy = O.q_sample(sched, x0, t, noise)   # bit-exact restatement of ddpm.py:356-359 (pinned by the tiny golden)
+    control = cn(hint=hint, timesteps=t, context=ctx)
+    eps = unet(x=x_noisy, timesteps=t, context=ctx, control=[c for c in control], only_mid_control=False)
+    loss = ((eps - noise) ** 2).mean([1, 2, 3]).mean()   # get_loss('l2', mean=False).mean([1,2,3]).mean(), ddpm.py:902-918
+    print("forward", time.time() - t0, flush=True)
+    loss.backward()
+    print("backward", time.time() - t0, flush=True)
+    names = [n for n, _ in cn.named_parameters()
+             if "lora_layer" in n or "zero_convs" in n or "middle_block_out" in n or "norm" in n]
+    grads = dict(cn.named_parameters())
+    g = {"seed": seed, "B": B, "t": t, "loss": loss.detach().clone(), "eps": eps.detach().clone(),
+         "trainable_names": names, "grad_norms": {n: grads[n].grad.norm().item() for n in names}}
+    keep = [n for n in names if n.startswith(("zero_convs.0.", "middle_block_out.0.bias", "input_blocks.1.1.norm",
+                                               "input_blocks.1.1.transformer_blocks.0.attn1.to_q.lora_layer.down",
+                                               "input_blocks.8.1.transformer_blocks.0.norm2",
+                                               "middle_block.1.transformer_blocks.0.attn2.to_v.lora_layer.up",
+                                               "time_embed.0.lora_layer.up"))]
+    g["grads"] = {n: grads[n].grad.clone() for n in keep}
+    out = os.path.join(GOLD, "sd15_rank128_train_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB", "in", time.time() - t0, "s")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--variants", action="store_true")
+    ap.add_argument("--full-train", action="store_true")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    full() if a.full else tiny()
+    if a.full:
+        full()
+    elif a.variants:
+        variants()
+    elif a.full_train:
+        full_train()
+    else:
+        tiny()
