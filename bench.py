@@ -261,6 +261,90 @@ def run_train(args, rank, local_rank, world, device):
                          "note": "algorithmically necessary 2.11 TFLOP/image (no recompute, no frozen weight grads)"}}
 
 
+PRETRAIN_BATCH = 8
+TF_PER_IMAGE_PRETRAIN = 2.33  # the finetune step's 2.11 TF + dense weight gradients of every ControlNet conv / linear
+# (= their forward cost: conv 122.4 + Linear 95.8 GF) -- algorithmically necessary work per image
+
+
+def run_pretrain(args, rank, local_rank, world, device):
+    """BASELINE.json configs[3]: ctrlora_pretrain_sd15_9tasks_rank128, one task per mini-batch from the multi-task
+    schedule (per-rank un-seeded permutations in the reference -> ranks generally train different tasks in a step), batch 8
+    per GPU (global 64 on 8 GPUs).  All ControlNet parameters + the task's LoRA set are trained."""
+    import numpy as np
+    import torch.distributed as dist
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from ctrlora_b200.scheduler import TaskSchedule
+    from ctrlora_b200.train import PretrainTrainer
+    cfg = os.path.join(ROOT, "configs", "ctrlora_pretrain_sd15_9tasks_rank128.yaml")
+    model = build_model(device, seed=0, config=cfg)
+    trainer = PretrainTrainer(model, lr=1e-5)
+    B = PRETRAIN_BATCH
+    gen = torch.Generator().manual_seed(300 + rank)
+    host = {"x0": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "hint": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory(),
+            "ctx": torch.randn(B, CTX_TOKENS, CTX_DIM, generator=gen).pin_memory(),
+            "t": torch.randint(0, 1000, (B,), generator=gen).pin_memory(),
+            "noise": torch.randn(B, 4, LATENT, LATENT, generator=gen).pin_memory()}
+    order = ("x0", "hint", "ctx", "t", "noise")
+    dev = [host[k].to(device) for k in order]
+    trainer.capture(*dev)  # one graph per task, shared memory pool
+    np.random.seed(1000 + rank)  # a different permutation stream per rank, like the reference's un-seeded ranks
+    sched = TaskSchedule(trainer.tasks, largest_dataset_size=B * 64, batch_size=B)
+    tasks = []
+    while len(tasks) < args.warmup + 2 * args.steps + 4:
+        tasks += list(sched)
+    it = iter(tasks)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        trainer.step(*dev, task=next(it))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(*dev, task=next(it))
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    loss_host = torch.empty(1).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in order)
+    for _ in range(2):
+        trainer.step(*[host[k].to(device, non_blocking=True) for k in order], task=next(it))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(*[host[k].to(device, non_blocking=True) for k in order], task=next(it))
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    peak_tf, _, peak_src = measured_peaks()
+    ips = world * B * args.steps / (ms_dev / 1e3)
+    lay = trainer.layout
+    return {"metric": "pretrain_images_per_sec", "value": ips, "unit": "images/s (512x512, 9 tasks, rank 128)",
+            "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms_dev / args.steps, "loss": float(loss_host.item()),
+            "tasks": len(trainer.tasks), "skipped_steps": trainer.skipped_steps,
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "trainable_params": trainer.G.numel, "controlnet_params": lay["base"][1],
+            "allreduce_bytes_per_step": (4 * (lay["base"][1] + min(world, len(trainer.tasks)) * lay["lora"][trainer.tasks[0]][1])
+                                         if world > 1 else 0),
+            "roofline": {"bound": "tensor", "achieved": ips / world * TF_PER_IMAGE_PRETRAIN, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ips / world * TF_PER_IMAGE_PRETRAIN / peak_tf, "peak_source": peak_src,
+                         "note": "algorithmically necessary 2.33 TFLOP/image (finetune step + dense ControlNet weight gradients)"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,7 +355,7 @@ def main():
     ap.add_argument("--lora-rank", type=int, default=128, choices=[32, 64, 128, 256, 512],
                     help="training workload only: BASELINE.json configs[4] rank sweep (default: the rank-128 headline)")
     ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH, help="training workload: images per GPU per step")
-    ap.add_argument("--workload", default="sample+train", choices=["sample", "train", "sample+train"],
+    ap.add_argument("--workload", default="sample+train", choices=["sample", "train", "sample+train", "pretrain"],
                     help="sample: configs[1] DDIM step (the headline line); train: configs[2] finetune step; default: both, "
                          "the training result rides in the line's 'train' key")
     args = ap.parse_args()
@@ -288,6 +372,20 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from ctrlora_b200 import dropin, ops
     dropin.activate()
+    if args.workload == "pretrain":
+        res = run_pretrain(args, rank, local_rank, world, device)
+        if rank == 0:
+            line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "fp16 (fp32 accumulate, fp32 master weights)", "data": "synthetic",
+                    "config": {"workload": "configs[3]: ctrlora_pretrain_sd15_9tasks_rank128, multi-task schedule, batch 8 per "
+                                           "GPU (global 64 on 8 GPUs), 512x512 (latent 4x64x64)",
+                               "batch_per_gpu": PRETRAIN_BATCH, "parallelism": f"dp{world}"},
+                    "e2e": res["e2e"], "roofline": res["roofline"], "pretrain": res}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "train":
         res = run_train(args, rank, local_rank, world, device)
         if rank == 0:

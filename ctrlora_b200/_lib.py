@@ -94,9 +94,13 @@ _ARGTYPES = {
     "ctrlora_adamw_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P],
     "ctrlora_nonfinite_flag_f32": [_P, _L, _P, _P],
     "ctrlora_im2col_3x3_f16": [_P, _P, _I, _I, _I, _I, _P],
-    "ctrlora_outer_accum_f32": [_P, _I, _P, _I, _P, _L, _I, _I, _I, _F, _F, _P],
+    "ctrlora_outer_accum_f32": [_P, _I, _P, _I, _P, _L, _I, _I, _I, _F, _F, _I, _P],
+    "ctrlora_copy2d_f32": [_P, _L, _P, _L, _L, _I, _I, _P],
     "ctrlora_silu_bwd_f32": [_P, _P, _P, _L, _P],
     "ctrlora_cast_rows_f32_to_f16": [_P, _L, _P, _L, _I, _P],
+    "ctrlora_im2col_s2_pad_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ctrlora_softmax_rows_f32_to_f16": [_P, _L, _P, _L, _L, _I, _F, _P],
+    "ctrlora_gaussian_sample": [_P, _P, _P, _I, _I, _I, _F, _P],
     "ctrlora_q_sample": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "ctrlora_ddim_encode_update": [_P, _P, _P, _P, _I, _F, _F, _F, _P],
     "ctrlora_weighted_sum_f16": [_P, _P, _I, _P, _L, _P],
@@ -152,8 +156,12 @@ EXPORTS = [
     "ctrlora_nonfinite_flag_f32",
     "ctrlora_weighted_sum_f16",
     "ctrlora_q_sample",
+    "ctrlora_im2col_s2_pad_f16",
+    "ctrlora_softmax_rows_f32_to_f16",
+    "ctrlora_gaussian_sample",
     "ctrlora_im2col_3x3_f16",
     "ctrlora_outer_accum_f32",
+    "ctrlora_copy2d_f32",
     "ctrlora_silu_bwd_f32",
     "ctrlora_cast_rows_f32_to_f16",
     "ctrlora_ddim_encode_update",

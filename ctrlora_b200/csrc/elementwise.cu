@@ -104,7 +104,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restri
 }
 
 // ---- stride-2 3x3 pad-1 gather: col[b, oh, ow, tap, c] = x[b, 2*oh + kh - 1, 2*ow + kw - 1, c] (0 outside)
-__global__ void im2col_s2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int vecs) {
+__global__ void im2col_s2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int vecs,
+                                 int pad_lo) {
     const int Ho = H / 2, Wo = W / 2;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(B) * Ho * Wo * 9 * vecs;
@@ -117,10 +118,67 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ src, uint4* __restric
     r /= Wo;
     const int oh = static_cast<int>(r % Ho);
     const int b = static_cast<int>(r / Ho);
-    const int ih = 2 * oh + tap / 3 - 1, iw = 2 * ow + tap % 3 - 1;
+    // pad_lo = 1: Conv2d(stride 2, padding 1) (openaimodel.py Downsample); pad_lo = 0: the VAE's F.pad(x, (0,1,0,1)) + Conv2d(
+    // stride 2, padding 0) (ldm/modules/diffusionmodules/model.py:80-84) -- zeros only on the right / bottom
+    const int ih = 2 * oh + tap / 3 - pad_lo, iw = 2 * ow + tap % 3 - pad_lo;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = src[((static_cast<long long>(b) * H + ih) * W + iw) * vecs + v];
     dst[i] = val;
+}
+
+// ---- row softmax of fp32 logits -> fp16 probabilities (the VAE's single-head AttnBlock at d = 512, model.py:179-203: logits
+// stay fp32 like the reference's bmm; one warp per row, two passes over a row that stays in L1/L2)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ src, long long lds, __half* __restrict__ dst, long long ldd, long long rows,
+                    int cols, float scale) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = src + row * lds;
+    float m = -3.0e38f;
+    for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + c);
+        m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float ms = m * scale;
+    float sum = 0.f;
+    for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + c);
+        sum += __expf(v.x * scale - ms) + __expf(v.y * scale - ms) + __expf(v.z * scale - ms) + __expf(v.w * scale - ms);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __half* y = dst + row * ldd;
+    for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + c);
+        __half2 h0 = __floats2half2_rn(__expf(v.x * scale - ms) * inv, __expf(v.y * scale - ms) * inv);
+        __half2 h1 = __floats2half2_rn(__expf(v.z * scale - ms) * inv, __expf(v.w * scale - ms) * inv);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(y + c) = u;
+    }
+}
+
+// ---- DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-37) on fp32 NCHW moments [B, 2Z, HW]:
+// mean = first Z channels, logvar = clamp(second Z channels, -30, 20); out = scale * (mean + exp(0.5 logvar) * noise), or
+// scale * mean when noise == NULL (.mode()).
+__global__ void gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float* __restrict__ out,
+                                       int B, int Z, int HW, float scale) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * Z * HW;
+    if (i >= total) return;
+    const long long b = i / (static_cast<long long>(Z) * HW), r = i % (static_cast<long long>(Z) * HW);
+    const float mean = moments[b * 2 * Z * HW + r];
+    float v = mean;
+    if (noise) {
+        const float lv = fminf(fmaxf(moments[b * 2 * Z * HW + static_cast<long long>(Z) * HW + r], -30.0f), 20.0f);
+        v = __fadd_rn(mean, __fmul_rn(expf(0.5f * lv), noise[i]));
+    }
+    out[i] = __fmul_rn(scale, v);
 }
 
 // ---- weight preparation: fp32 [batch, R, C] -> fp16 [batch, C, R]  (Conv2d [Cout, Cin, 3*3] -> [Cout, 9, Cin];
@@ -346,7 +404,33 @@ extern "C" int ctrlora_im2col_s2_f16(const void* src, void* dst, int batch, int 
     const int vecs = channels / 8;
     const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * vecs;
     im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(src),
-                                                                       reinterpret_cast<uint4*>(dst), batch, h, w, vecs);
+                                                                       reinterpret_cast<uint4*>(dst), batch, h, w, vecs, 1);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_im2col_s2_pad_f16(const void* src, void* dst, int batch, int h, int w, int channels, int pad_lo,
+                                         void* stream) {
+    if (!src || !dst || channels % 8 != 0 || (h & 1) || (w & 1) || pad_lo < 0 || pad_lo > 1) return CTRLORA_ERR_ARG;
+    const int vecs = channels / 8;
+    const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * vecs;
+    im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const uint4*>(src),
+                                                                       reinterpret_cast<uint4*>(dst), batch, h, w, vecs, pad_lo);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_softmax_rows_f32_to_f16(const float* src, long long lds, void* dst, long long ldd, long long rows,
+                                               int cols, float scale, void* stream) {
+    if (!src || !dst || cols % 4 != 0 || lds % 4 != 0 || ldd % 4 != 0) return CTRLORA_ERR_ARG;
+    softmax_rows_kernel<<<blocks_for(rows, 8), 256, 0, STREAM(stream)>>>(src, lds, reinterpret_cast<__half*>(dst), ldd, rows,
+                                                                       cols, scale);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_gaussian_sample(const float* moments, const float* noise, float* out, int batch, int z_channels, int hw,
+                                       float scale, void* stream) {
+    if (!moments || !out) return CTRLORA_ERR_ARG;
+    const long long total = static_cast<long long>(batch) * z_channels * hw;
+    gaussian_sample_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(moments, noise, out, batch, z_channels, hw, scale);
     return LAUNCH_OK();
 }
 

@@ -251,14 +251,18 @@ __global__ void im2col_3x3_kernel(const uint4* __restrict__ src, uint4* __restri
 // MLP / emb_layers linears, where the "token" dimension is just the batch
 __global__ void __launch_bounds__(256)
 outer_accum_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx, float* __restrict__ out,
-                   long long ldo, int rows, int N, int K, float alpha, float beta) {
+                   long long ldo, int rows, int N, int K, float alpha, float beta, int silu_x) {
     pdl_launch_dependents();
     pdl_wait();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = blockIdx.y;
     if (k >= K) return;
     float acc = 0.f;
-    for (int b = 0; b < rows; ++b) acc += dy[b * lddy + n] * x[b * ldx + k];
+    for (int b = 0; b < rows; ++b) {
+        float xv = x[b * ldx + k];
+        if (silu_x) xv = xv / (1.0f + __expf(-xv));
+        acc += dy[b * lddy + n] * xv;
+    }
     float* o = out + n * ldo + k;
     *o = beta * (*o) + alpha * acc;
 }
@@ -272,6 +276,20 @@ __global__ void silu_bwd_kernel(const float* __restrict__ d, const float* __rest
     const float z = x[i];
     const float s = 1.0f / (1.0f + __expf(-z));
     out[i] = d[i] * s * (1.0f + z * (1.0f - s));
+}
+
+// dst[r, c] (+)= src[r, c] over [rows, cols] with row strides (fp32): sub-block extraction of padded gradient tiles
+__global__ void copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, long long rows,
+                              int cols, int accumulate) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols;
+    const int c = static_cast<int>(i % cols);
+    const float v = src[r * lds + c];
+    float* d = dst + r * ldd + c;
+    *d = accumulate ? *d + v : v;
 }
 
 // fp32 [rows, cols] with arbitrary row stride -> fp16 dense (weight copies of parameters stored in kernel layout)
@@ -400,10 +418,18 @@ extern "C" int ctrlora_im2col_3x3_f16(const void* src, void* dst, int batch, int
 }
 
 extern "C" int ctrlora_outer_accum_f32(const float* dy, int lddy, const float* x, int ldx, float* out, long long ldo, int rows,
-                                       int n, int k, float alpha, float beta, void* stream) {
+                                       int n, int k, float alpha, float beta, int silu_x, void* stream) {
     if (!dy || !x || !out || rows < 1 || n < 1 || k < 1) return CTRLORA_ERR_ARG;
     launch_pdl(outer_accum_kernel, dim3((k + 255) / 256, n), dim3(256), (size_t)0, STREAM(stream), dy, lddy, x, ldx, out, ldo,
-               rows, n, k, alpha, beta);
+               rows, n, k, alpha, beta, silu_x);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                                  int accumulate, void* stream) {
+    if (!src || !dst) return CTRLORA_ERR_ARG;
+    launch_pdl(copy2d_kernel, dim3(nblk(rows * cols, 256)), dim3(256), (size_t)0, STREAM(stream), src, lds, dst, ldd, rows, cols,
+               accumulate);
     return LAUNCH_OK();
 }
 

@@ -184,9 +184,21 @@ class ControlLDM(LatentDiffusion):
         """`0.18215 * VAE.encode(hint).sample()` (cldm_ctrlora_finetune.py:76-77).  A 4-channel tensor is taken to be
         that latent already (the reference would fail on it), which is how the post-VAE parity boundary and the
         benchmarks feed the path."""
-        hint = torch.cat(c_concat, 1)
+        hint = c_concat[0] if len(c_concat) == 1 else torch.cat(c_concat, 1)
         if hint.shape[1] == self.channels:
             return hint
+        if getattr(self, "cache_hint_latent", False):
+            # Opt-in (SURVEY.md §8 f1): the reference re-encodes the SAME condition image and re-draws posterior noise in
+            # every apply_model -- 2 x S VAE passes of 1117 GFLOP per sampled image.  With the cache the latent is encoded
+            # and sampled once per distinct hint tensor; that changes how much host RNG a sampling run consumes (one draw
+            # instead of 2 x S), which is why it is not the default.
+            key = (hint.data_ptr(), hint._version, tuple(hint.shape))
+            hit = self.__dict__.get("_hint_cache")
+            if hit is not None and hit[0] == key:
+                return hit[1]
+            lat = self.get_first_stage_encoding(self.encode_first_stage(hint))
+            self.__dict__["_hint_cache"] = (key, lat)
+            return lat
         return self.get_first_stage_encoding(self.encode_first_stage(hint))
 
     def scaled_control(self, control):

@@ -155,6 +155,11 @@ class LatentDiffusion(DDPM):
         return self.first_stage_model.encode(x)
 
     def get_first_stage_encoding(self, encoder_posterior):
+        """scale_factor * posterior.sample() (reference ddpm.py get_first_stage_encoding): the drop-in posterior draws the
+        noise like the reference (host RNG) and applies mean + std * noise and the scale in one kernel."""
+        from ldm.modules.distributions.distributions import DiagonalGaussianDistribution
+        if isinstance(encoder_posterior, DiagonalGaussianDistribution):
+            return encoder_posterior.sample(scale=self.scale_factor)
         z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
         return self.scale_factor * z
 
@@ -162,6 +167,9 @@ class LatentDiffusion(DDPM):
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         if self.first_stage_model is None:
             raise RuntimeError("no first_stage_model available to decode latents")
+        from ldm.models.autoencoder import AutoencoderKL
+        if isinstance(self.first_stage_model, AutoencoderKL):
+            return self.first_stage_model.decode(z, in_scale=1. / self.scale_factor)  # folded into post_quant_conv's weights
         return self.first_stage_model.decode(1. / self.scale_factor * z)
 
     def get_learned_conditioning(self, c):

@@ -399,14 +399,41 @@ def upsample2x(x):
     return y
 
 
-def im2col_s2(x):
+def im2col_s2(x, pad_lo=1):
+    """stride-2 3x3 gather; pad_lo=1: Conv2d(padding=1); pad_lo=0: zeros on the right/bottom only (the VAE's Downsample)"""
     _require_cuda(x)
     assert x.is_contiguous() and x.dtype == torch.float16
     b, h, w, c = x.shape
     y = torch.empty((b, h // 2, w // 2, 9 * c), device=x.device, dtype=torch.float16)
     _count(1)
-    check(_lib.load().ctrlora_im2col_s2_f16(_dp(x), _dp(y), b, h, w, c, _sp()), "im2col_s2")
+    check(_lib.load().ctrlora_im2col_s2_pad_f16(_dp(x), _dp(y), b, h, w, c, int(pad_lo), _sp()), "im2col_s2")
     return y
+
+
+def softmax_rows(logits, scale=1.0):
+    """fp32 [rows, cols] -> fp16 softmax(scale * logits) over the last dim"""
+    _require_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    out = torch.empty(logits.shape, device=logits.device, dtype=torch.float16)
+    _count(1)
+    check(_lib.load().ctrlora_softmax_rows_f32_to_f16(_dp(logits), logits.stride(0), _dp(out), out.stride(0), logits.shape[0],
+                                                      logits.shape[1], float(scale), _sp()), "softmax_rows")
+    return out
+
+
+def gaussian_sample(moments, noise=None, scale=1.0):
+    """moments fp32 [B, 2Z, H, W] -> scale * (mean + std * noise) (noise None: scale * mean), fp32 [B, Z, H, W]"""
+    _require_cuda(moments, noise)
+    moments = moments.float().contiguous()
+    b, z2, h, w = moments.shape
+    out = torch.empty((b, z2 // 2, h, w), device=moments.device, dtype=torch.float32)
+    if noise is not None:
+        noise = noise.float().contiguous()
+        assert noise.shape == out.shape
+    _count(1)
+    check(_lib.load().ctrlora_gaussian_sample(_dp(moments), _dp(noise), _dp(out), b, z2 // 2, h * w, float(scale), _sp()),
+          "gaussian_sample")
+    return out
 
 
 def cast_transpose(src, batch, rows, cols, out=None):
@@ -447,8 +474,8 @@ def im2col_3x3(x):
     return y
 
 
-def outer_accum(dy, x, out, alpha=1.0, beta=1.0):
-    """out[n, k] = beta*out + alpha * sum_b dy[b, n] x[b, k]  (fp32 [B,N], [B,K] -> fp32 [N,K], row strides free)"""
+def outer_accum(dy, x, out, alpha=1.0, beta=1.0, silu_x=False):
+    """out[n, k] = beta*out + alpha * sum_b dy[b, n] f(x[b, k])  (fp32 [B,N], [B,K] -> fp32 [N,K], row strides free)"""
     _require_cuda(dy, x, out)
     assert dy.dtype == x.dtype == out.dtype == torch.float32 and dy.stride(1) == 1 and x.stride(1) == 1 and out.stride(1) == 1
     rows, n = dy.shape
@@ -456,8 +483,17 @@ def outer_accum(dy, x, out, alpha=1.0, beta=1.0):
     assert x.shape[0] == rows and out.shape == (n, k)
     _count()
     check(_lib.load().ctrlora_outer_accum_f32(_dp(dy), dy.stride(0), _dp(x), x.stride(0), _dp(out), out.stride(0), rows, n, k,
-                                              float(alpha), float(beta), _sp()), "outer_accum")
+                                              float(alpha), float(beta), int(silu_x), _sp()), "outer_accum")
     return out
+
+
+def copy2d(src, dst, rows, cols, lds, ldd, accumulate=False):
+    """dst[r, c] (+)= src[r, c] over fp32 [rows, cols] blocks with explicit row strides"""
+    _require_cuda(src, dst)
+    assert src.dtype == dst.dtype == torch.float32
+    _count()
+    check(_lib.load().ctrlora_copy2d_f32(_dp(src), lds, _dp(dst), ldd, rows, cols, int(accumulate), _sp()), "copy2d")
+    return dst
 
 
 def silu_bwd(d, x):

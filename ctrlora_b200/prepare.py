@@ -60,7 +60,12 @@ def linear_weight(weight):
 def conv_weight(weight, pad_in=None, pad_out=None):
     """nn.Conv2d weight fp32 [Cout, Cin, kh, kw] -> fp16 [Cout(pad), kh*kw, Cin(pad)] (tap-major, channel-minor)."""
     co, ci, kh, kw = weight.shape
-    w = ops.cast_transpose(_f32c(weight), co, ci, kh * kw)  # [Cout, taps, Cin]
+    wk = weight.detach().permute(0, 2, 3, 1)
+    if weight.dtype == torch.float32 and wk.is_contiguous() and weight.is_cuda:
+        # a trainer's GradSink already stores the parameter in kernel order [Cout, kh, kw, Cin]: the copy is a plain cast
+        w = ops.cast_transpose(wk, co * kh * kw * ci, 1, 1).view(co, kh * kw, ci)
+    else:
+        w = ops.cast_transpose(_f32c(weight), co, ci, kh * kw)  # [Cout, taps, Cin]
     if pad_in or pad_out:
         full = torch.zeros((pad_out or co, kh * kw, pad_in or ci), device=w.device, dtype=torch.float16)
         full[:co, :, :ci] = w

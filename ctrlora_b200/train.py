@@ -26,16 +26,23 @@ f32 = prepare.bias_f32
 
 # ------------------------------------------------------------------------------------------------ gradient sink
 class GradSink:
-    """Flat fp32 buffers (params, grads, Adam moments) over the optimizer's parameter set, in the reference's order."""
+    """Flat fp32 buffers (params, grads, Adam moments) over an optimizer's parameter set.
 
-    def __init__(self, control_model):
-        from cldm.cldm_ctrlora_finetune import trainable_parameters
-        if not getattr(control_model, "ft_with_lora", True):
-            # full-ControlNet finetuning selects every parameter (cldm_ctrlora_finetune.py:101-104); this sink's backward
-            # only produces LoRA / zero-conv / norm gradients -- stepping the rest would be pure weight decay
-            raise NotImplementedError("FinetuneTrainer covers ft_with_lora=True; use PretrainTrainer (dense weight "
-                                      "gradients of every ControlNet parameter) for full-parameter training")
-        named = trainable_parameters(control_model)
+    Default set: the finetune filter in the reference's order (cldm_ctrlora_finetune.py:88-100).  `named` overrides it
+    (PretrainSink).  Conv weights are STORED in the kernels' [Cout, kh, kw, Cin] order -- the nn.Parameter keeps its
+    reference shape [Cout, Cin, kh, kw] as a permuted view of that storage -- so the dense weight-gradient GEMM writes its
+    [Cout, taps*Cin] result straight into the gradient buffer and the fp16 kernel copy is a plain cast; AdamW and the
+    all-reduce are elementwise over the flat buffers and never see the difference."""
+
+    def __init__(self, control_model, named=None):
+        if named is None:
+            from cldm.cldm_ctrlora_finetune import trainable_parameters
+            if not getattr(control_model, "ft_with_lora", True):
+                # full-ControlNet finetuning selects every parameter (cldm_ctrlora_finetune.py:101-104): that is the
+                # dense-gradient trainer's job -- this sink's backward would leave conv/linear gradients at zero
+                raise NotImplementedError("FinetuneTrainer covers ft_with_lora=True; use PretrainTrainer (dense weight "
+                                          "gradients of every ControlNet parameter) for full-parameter training")
+            named = trainable_parameters(control_model)
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         total = sum(p.numel() for p in self.params)
@@ -44,23 +51,34 @@ class GradSink:
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros_like(self.flat_g)
         self.exp_avg_sq = torch.zeros_like(self.flat_g)
-        self._grad = {}
+        self._grad, self._api_grad, self.offsets = {}, {}, {}
         off = 0
-        for p in self.params:
+        for name, p in zip(self.names, self.params):
             n = p.numel()
-            self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
-            p.data = self.flat_p[off:off + n].view(p.shape)  # the module now reads the flat buffer
+            seg_p, seg_g = self.flat_p[off:off + n], self.flat_g[off:off + n]
+            if p.dim() == 4:
+                co, ci, kh, kw = p.shape
+                seg_p.view(co, kh, kw, ci).copy_(p.detach().permute(0, 2, 3, 1))
+                p.data = seg_p.view(co, kh, kw, ci).permute(0, 3, 1, 2)   # reference shape, kernel-order storage
+                self._grad[id(p)] = seg_g.view(co, kh * kw * ci)
+                self._api_grad[id(p)] = seg_g.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                seg_p.copy_(p.detach().reshape(-1))
+                p.data = seg_p.view(p.shape)  # the module now reads the flat buffer
+                self._grad[id(p)] = self._api_grad[id(p)] = seg_g.view(p.shape)
             p._ctrlora_trainable = True
-            self._grad[id(p)] = self.flat_g[off:off + n].view(p.shape)
+            self.offsets[name] = (off, n)
             off += n
         self.numel = total
 
     def grad(self, param):
-        """fp32 gradient view of a trainable parameter, or None if the optimizer does not own it."""
+        """fp32 gradient view of a trainable parameter in STORAGE order (conv weights: [Cout, taps*Cin]), or None if the
+        optimizer does not own it."""
         return self._grad.get(id(param)) if param is not None else None
 
     def named_grads(self):
-        return {n: self._grad[id(p)] for n, p in zip(self.names, self.params)}
+        """{name: gradient} in the parameters' reference shapes"""
+        return {n: self._api_grad[id(p)] for n, p in zip(self.names, self.params)}
 
     def zero(self):
         self.flat_g.zero_()
@@ -123,6 +141,54 @@ def lora_grads(lin, x2d, dy2d, G):
     ops.wgrad_tn(t2, x2d, out=g_down, alpha=scale, beta=1.0)
 
 
+def dense_lin_grads(lin, x2d, dy2d, G):
+    """Dense dW = dY^T X and db = colsum(dY) of an nn.Linear when the optimizer owns them (pretraining: every ControlNet
+    parameter, cldm_ctrlora_pretrain.py:174-182); no-op for the finetune set."""
+    if G is None:
+        return
+    gw = G.grad(lin.weight)
+    if gw is not None:
+        ops.wgrad_tn(dy2d, x2d, out=gw, beta=1.0)
+    gb = G.grad(getattr(lin, "bias", None))
+    if gb is not None:
+        ops.colsum(dy2d, gb)
+
+
+def lin_grads(lin, x2d, dy2d, G):
+    lora_grads(lin, x2d, dy2d, G)
+    dense_lin_grads(lin, x2d, dy2d, G)
+
+
+def dense_conv_grads(conv, xp, dyp, G, col=None):
+    """Dense weight / bias gradients of a conv whose (pixel-major fp16) input was xp and output gradient is dyp.
+    3x3: dW[Cout, tap, Cin] = dY^T im2col(x) -- exactly the gradient buffer's storage order (GradSink); 1x1: dY^T X.
+    `col`: the already gathered operand (stride-2 Downsample keeps its forward gather)."""
+    if G is None:
+        return
+    gw = G.grad(conv.weight)
+    if gw is not None:
+        b, h, w, co = dyp.shape
+        d2d = dyp.reshape(b * h * w, co)
+        if col is None:
+            if conv.kernel_size[0] == 1:
+                col = xp.reshape(b * h * w, -1)
+            else:
+                col = ops.im2col_3x3(xp.contiguous()).view(b * h * w, -1)
+        else:
+            col = col.reshape(b * h * w, -1)
+        cin_store = gw.shape[1] // (conv.kernel_size[0] * conv.kernel_size[1])
+        cin_x = col.shape[1] // (conv.kernel_size[0] * conv.kernel_size[1])
+        if cin_x == cin_store:
+            ops.wgrad_tn(d2d, col, out=gw, beta=1.0)
+        else:  # channel-padded input (the 4-channel latent conv runs on 8): drop the padding columns
+            tmp = ops.wgrad_tn(d2d, col)
+            taps = conv.kernel_size[0] * conv.kernel_size[1]
+            ops.copy2d(tmp, gw, co * taps, cin_store, cin_x, cin_store, accumulate=True)
+    gb = G.grad(conv.bias)
+    if gb is not None:
+        ops.colsum(dyp.reshape(-1, dyp.shape[-1]), gb)
+
+
 # ------------------------------------------------------------------------------------------------ transformer block
 def tblock_fwd(blk, x2d, batch, n, ctx2d, nk):
     dev = x2d.device
@@ -181,32 +247,32 @@ def tblock_bwd(blk, s, d_x3, G):
 
     proj, out = ff.net[0].proj, ff.net[2]
     d_g = ops.gemm(d_x3, lin_wT(out))
-    lora_grads(out, s["g"], d_x3, G)
+    lin_grads(out, s["g"], d_x3, G)
     d_h = ops.geglu_bwd(s["h"], d_g)
     d_n3 = ops.gemm(d_h, lin_wT(proj))
-    lora_grads(proj, s["n3"], d_h, G)
+    lin_grads(proj, s["n3"], d_h, G)
     d_x2 = ln_bwd(blk.norm3, s["x2"], d_n3, d_x3)
     # ---- cross attention
     o2 = a2m.to_out[0]
     d_a2 = ops.gemm(d_x2, lin_wT(o2))
-    lora_grads(o2, s["a2"], d_x2, G)
+    lin_grads(o2, s["a2"], d_x2, G)
     dq2, dk2, dv2 = ops.attention_bwd(s["q2"], s["k2"], s["v2"], s["a2"], d_a2, s["lse2"], batch, heads, n, nk, d)
     d_n2 = ops.gemm(dq2, lin_wT(a2m.to_q))
-    lora_grads(a2m.to_q, s["n2"], dq2, G)
-    lora_grads(a2m.to_k, ctx2d, dk2, G)
-    lora_grads(a2m.to_v, ctx2d, dv2, G)
+    lin_grads(a2m.to_q, s["n2"], dq2, G)
+    lin_grads(a2m.to_k, ctx2d, dk2, G)
+    lin_grads(a2m.to_v, ctx2d, dv2, G)
     d_x1 = ln_bwd(blk.norm2, s["x1"], d_n2, d_x2)
     # ---- self attention
     o1 = a1m.to_out[0]
     d_a1 = ops.gemm(d_x1, lin_wT(o1))
-    lora_grads(o1, s["a1"], d_x1, G)
+    lin_grads(o1, s["a1"], d_x1, G)
     dqkv = torch.empty((batch * n, 3 * inner), device=d_x3.device, dtype=torch.float16)
     ops.attention_bwd(s["q1"], s["k1"], s["v1"], s["a1"], d_a1, s["lse1"], batch, heads, n, n, d, dq=dqkv[:, :inner],
                       dk=dqkv[:, inner:2 * inner], dv=dqkv[:, 2 * inner:])
     d_n1 = ops.gemm(dqkv, cat_wT(a1m, "qkv", [a1m.to_q, a1m.to_k, a1m.to_v]))
-    lora_grads(a1m.to_q, s["n1"], dqkv[:, :inner], G)
-    lora_grads(a1m.to_k, s["n1"], dqkv[:, inner:2 * inner], G)
-    lora_grads(a1m.to_v, s["n1"], dqkv[:, 2 * inner:], G)
+    lin_grads(a1m.to_q, s["n1"], dqkv[:, :inner], G)
+    lin_grads(a1m.to_k, s["n1"], dqkv[:, inner:2 * inner], G)
+    lin_grads(a1m.to_v, s["n1"], dqkv[:, 2 * inner:], G)
     return ln_bwd(blk.norm1, s["x"], d_n1, d_x1)
 
 
@@ -224,15 +290,17 @@ def st_fwd(st, x, ctx):
         y2d, bs = tblock_fwd(blk, y2d, b, h * w, ctx2d, nk)
         blocks.append(bs)
     out = ops.gemm(y2d.view(b, h, w, -1), conv_w(st.proj_out), bias=f32(st.proj_out.bias), residual=xp.view(b * h * w, c))
-    return nchw_view(out), {"xp": xp, "stats": stats, "blocks": blocks, "shape": (b, h, w, c)}
+    return nchw_view(out), {"xp": xp, "stats": stats, "blocks": blocks, "shape": (b, h, w, c), "xn": xn, "y_last": y2d}
 
 
 def st_bwd(st, s, d_out, G):
     b, h, w, c = s["shape"]
     dop = pixel_major(d_out)
+    dense_conv_grads(st.proj_out, s["y_last"].view(b, h, w, -1), dop, G)
     d_y = ops.gemm(dop, conv_wd(st.proj_out)).view(b * h * w, -1)
     for blk, bs in zip(reversed(st.transformer_blocks), reversed(s["blocks"])):
         d_y = tblock_bwd(blk, bs, d_y, G)
+    dense_conv_grads(st.proj_in, s["xn"], d_y.view(b, h, w, -1), G)
     d_xn = ops.gemm(d_y.view(b, h, w, -1), conv_wd(st.proj_in))
     gn = prepare.effective(st.norm)
     gw, gb = (G.grad(gn.weight), G.grad(gn.bias)) if G is not None else (None, None)
@@ -268,26 +336,42 @@ def res_fwd(rb, x, rowbias):
         out = ops.gemm(c, conv_w(conv2), ksize=3, bias=bsum, a2=xp, w2=wsk)
     else:
         out = ops.gemm(c, conv_w(conv2), ksize=3, bias=f32(conv2.bias), residual=xp.view(b * h * w, cin))
-    s.update(src=src, stats1=stats1, hmid=hmid, stats2=stats2, shape=(b, h, w, cin))
+    s.update(src=src, stats1=stats1, hmid=hmid, stats2=stats2, shape=(b, h, w, cin), a=a, c=c, xp=xp)
     return nchw_view(out), s
 
 
-def res_bwd(rb, s, d_out, rowbias_grad=None, want_dx2=False, dx1_scale=1.0):
+def res_bwd(rb, s, d_out, rowbias_grad=None, want_dx2=False, dx1_scale=1.0, G=None):
     """Returns dx1 (times dx1_scale) and, if want_dx2, the gradient of the second concat half times its add2_scale."""
     gn1, conv1, gn2, conv2 = rb.in_layers[0], rb.in_layers[2], rb.out_layers[0], rb.out_layers[3]
     skip = None if isinstance(rb.skip_connection, nn.Identity) else rb.skip_connection
     b, h, w, cin = s["shape"]
     dop = pixel_major(d_out)
+    if G is not None:  # dense conv gradients + GroupNorm affine gradients (pretraining owns them; the finetune set owns
+        # neither: ResBlock norms are named in_layers.0 / out_layers.0, which the 'norm' filter does not match)
+        dense_conv_grads(conv2, s["c"], dop, G)
+        if skip is not None:
+            gw = G.grad(skip.weight)
+            if gw is not None:
+                ops.wgrad_tn(dop.reshape(b * h * w, -1), s["xp"].reshape(b * h * w, cin), out=gw, beta=1.0)
+            # conv2.bias and skip.bias receive the same gradient (their sum is the fused epilogue bias)
+            gb = G.grad(skip.bias)
+            if gb is not None:
+                ops.colsum(dop.reshape(b * h * w, -1), gb)
     d_c = ops.gemm(dop, conv_wd(conv2), ksize=3)
     d_skip = ops.gemm(dop, conv_wd(skip)).view(b * h * w, cin) if skip is not None else dop.view(b * h * w, cin)
-    d_hmid = ops.groupnorm_bwd(d_c, s["stats2"], s["hmid"], f32(gn2.weight), f32(gn2.bias), gn2.eps, True)
+    g2w, g2b = (G.grad(gn2.weight), G.grad(gn2.bias)) if G is not None else (None, None)
+    d_hmid = ops.groupnorm_bwd(d_c, s["stats2"], s["hmid"], f32(gn2.weight), f32(gn2.bias), gn2.eps, True, dgamma=g2w, dbeta=g2b)
     if rowbias_grad is not None:
         ops.image_colsum(d_hmid.view(b * h * w, -1), b, rowbias_grad)
+    if G is not None:
+        dense_conv_grads(conv1, s["a"], d_hmid, G)
     d_a = ops.gemm(d_hmid, conv_wd(conv1), ksize=3)
     src = s["src"]
+    g1w, g1b = (G.grad(gn1.weight), G.grad(gn1.bias)) if G is not None else (None, None)
     res = ops.groupnorm_bwd(d_a, s["stats1"], src["x1"], f32(gn1.weight), f32(gn1.bias), gn1.eps, True, add1=src["add1"],
                             add1_scale=src["add1_scale"], x2=src["x2"], add2=src["add2"], add2_scale=src["add2_scale"],
-                            want_dx2=want_dx2, dx2_scale=src["add2_scale"], res=d_skip, dx1_scale=dx1_scale)
+                            want_dx2=want_dx2, dx2_scale=src["add2_scale"], res=d_skip, dx1_scale=dx1_scale,
+                            dgamma=g1w, dbeta=g1b)
     if want_dx2:
         return nchw_view(res[0]), nchw_view(res[1])
     return nchw_view(res)
@@ -299,11 +383,13 @@ def down_fwd(ds, x):
     b, h, w, c = xp.shape
     col = ops.im2col_s2(xp)
     wk = _cache(ds).get("w", [ds.op.weight], lambda: prepare.conv_weight(ds.op.weight).view(ds.out_channels, 1, 9 * c))
-    return nchw_view(ops.gemm(col, wk, bias=f32(ds.op.bias))), {"shape": (b, h, w, c)}
+    return nchw_view(ops.gemm(col, wk, bias=f32(ds.op.bias))), {"shape": (b, h, w, c), "col": col}
 
 
-def down_bwd(ds, s, d_out):
+def down_bwd(ds, s, d_out, G=None):
     b, h, w, c = s["shape"]
+    if G is not None:
+        dense_conv_grads(ds.op, None, pixel_major(d_out), G, col=s["col"])
     wk = _cache(ds).get("w", [ds.op.weight], lambda: prepare.conv_weight(ds.op.weight).view(ds.out_channels, 1, 9 * c))
     wt = _cache(ds).get("wT", [ds.op.weight], lambda: prepare.weight_T(wk))
     d_col = ops.gemm(pixel_major(d_out), wt)  # [B, h/2, w/2, 9*C]
@@ -340,8 +426,11 @@ def seq_fwd(seq, x, emb, ctx):
             x, s = up_fwd(layer, x)
             tape.append(("up", layer, s))
         elif isinstance(layer, _Conv):
-            x = layer(x)  # the 4-channel input conv: nothing upstream needs its gradient
-            tape.append(("stop", layer, None))
+            cin = layer.in_channels
+            c_pad = (cin + 7) // 8 * 8
+            xin = pixel_major(x, c_pad if c_pad != cin else None)
+            x = layer(nchw_view(xin))  # the 4-channel input conv: nothing upstream needs its data gradient
+            tape.append(("stop", layer, {"xin": xin}))
         else:
             raise NotImplementedError(type(layer))
     return x, tape
@@ -354,58 +443,73 @@ def seq_bwd(tape, d, G, emb_grads=None, first_res_kw=None):
         if kind == "res":
             kw = first_res_kw if (i == 0 and first_res_kw) else {}
             rg = emb_grads.get(id(mod)) if emb_grads is not None else None
-            d = res_bwd(mod, s, d, rowbias_grad=rg, **kw)
+            d = res_bwd(mod, s, d, rowbias_grad=rg, G=G, **kw)
         elif kind == "st":
             d = st_bwd(mod, s, d, G)
         elif kind == "down":
-            d = down_bwd(mod, s, d)
+            d = down_bwd(mod, s, d, G)
         elif kind == "up":
             d = up_bwd(mod, s, d)
         elif kind == "stop":
+            if G is not None:
+                dense_conv_grads(mod, s["xin"], pixel_major(d), G)
             return None
     return d
 
 
 # ------------------------------------------------------------------------------------------------ time-embedding MLP
-def emb_mlp_backward(net, t_emb, emb, d_slices, G):
-    """Gradients of time_embed.{0,2} and every emb_layers.1 LoRA pair from the per-ResBlock d(rowbias) (fp32 [B, Cout]).
-    M = batch rows only: plain torch fp32 matmuls (cuBLAS) -- see the module docstring."""
-    from ldm.modules.diffusionmodules.openaimodel import ResBlock
-
-    def lora_lin_bwd(lin, x, dy):
-        lora = getattr(lin, "lora_layer", None)
-        w = lin.weight.detach().float()
-        if lora is not None:
-            dwn, up = lora.down.weight.detach().float(), lora.up.weight.detach().float()
-            sc = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
-            gu, gd = G.grad(lora.up.weight), G.grad(lora.down.weight)
-            if gu is not None:
-                gu.add_(sc * dy.t() @ (x @ dwn.t()))
-                gd.add_(sc * (dy @ up).t() @ x)
-            w = w + sc * up @ dwn
-        return dy @ w
-
-    se = torch.nn.functional.silu(emb)
-    d_se = torch.zeros_like(emb)
-    for rb in (m for m in net.modules() if isinstance(m, ResBlock)):
-        d_se += lora_lin_bwd(rb.emb_layers[1], se, d_slices[id(rb)])
-    sig = torch.sigmoid(emb)
-    d_emb = d_se * sig * (1 + emb * (1 - sig))
-    l0, l2 = net.time_embed[0], net.time_embed[2]
-    hid_pre = torch.nn.functional.linear(t_emb, prepare_f32_weight(l0), l0.bias.detach().float())
-    hid = torch.nn.functional.silu(hid_pre)
-    d_hid = lora_lin_bwd(l2, hid, d_emb)
-    s0 = torch.sigmoid(hid_pre)
-    lora_lin_bwd(l0, t_emb, d_hid * s0 * (1 + hid_pre * (1 - s0)))
-
-
-def prepare_f32_weight(lin):
+def _small_lora_grads(lin, x, dy, G, silu_x=False):
+    """LoRA (and, when owned, dense) gradients of a linear whose 'token' dimension is the batch: fp32 [B, K] input x
+    (SiLU applied on the fly when silu_x), fp32 [B, N] output gradient dy.  cldm/lora.py:70-80,285-291."""
+    gw, gb = G.grad(lin.weight), G.grad(getattr(lin, "bias", None))
+    if gw is not None:
+        ops.outer_accum(dy, x, gw, silu_x=silu_x)
+    if gb is not None:
+        ops.colsum(dy, gb)
     lora = getattr(lin, "lora_layer", None)
-    w = lin.weight.detach().float()
-    if lora is not None:
-        sc = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
-        w = w + sc * lora.up.weight.detach().float() @ lora.down.weight.detach().float()
-    return w
+    if lora is None:
+        return
+    gu, gd = G.grad(lora.up.weight), G.grad(lora.down.weight)
+    if gu is None:
+        return
+    sc = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
+    r, k = lora.down.weight.shape
+    n = lora.up.weight.shape[0]
+    c = _cache(lora)
+    d16 = c.get("d16s", [lora.down.weight], lambda: prepare.linear_weight(lora.down.weight).view(r, k))           # [r, K]
+    u16t = c.get("u16ts", [lora.up.weight], lambda: ops.cast_transpose(f32(lora.up.weight), 1, n, r).view(r, n))  # [r, N]
+    t1 = ops.small_linear(x, d16, None, silu_in=silu_x)      # (f(x)) Down^T  [B, r]
+    ops.outer_accum(dy, t1, gu, alpha=sc)                    # dUp   += sc * dY^T (X Down^T)
+    t2 = ops.small_linear(dy, u16t, None)                    # dY Up          [B, r]
+    ops.outer_accum(t2, x, gd, alpha=sc, silu_x=silu_x)      # dDown += sc * (dY Up)^T X
+
+
+def emb_mlp_backward(net, t_emb, emb, d_all, slices, G):
+    """Backward of timestep_embedding -> time_embed (Linear, SiLU, Linear) -> every ResBlock's emb_layers (SiLU, Linear)
+    (openaimodel.py:526-531, :208-215; LoRA-wrapped in the ControlNet) from d_all = d(rowbias) [B, sum Cout] (fp32; slices =
+    {id(resblock): column view}).  M = batch rows: GEMV-shaped work on the small_linear / outer-product kernels."""
+    from ldm.modules.diffusionmodules.openaimodel import ResBlock
+    blocks = [m for m in net.modules() if isinstance(m, ResBlock)]
+    l0, l2 = net.time_embed[0], net.time_embed[2]
+    # weight / LoRA gradients of the emb_layers: input silu(emb), output gradient = the block's slice
+    for rb in blocks:
+        _small_lora_grads(rb.emb_layers[1], emb, slices[id(rb)], G, silu_x=True)
+    # d silu(emb) = d_all @ Wcat  (the forward's batched [sum Cout, 1280] matrix, transposed once per weight version)
+    lins = [b.emb_layers[1] for b in blocks]
+    params = [p for lin in lins for p in prepare.linear_params(lin)]
+    wcat_t = _cache(net).get("emb_cat_T", params, lambda: prepare.weight_T(
+        torch.cat([b.emb_weight() for b in blocks], 0).contiguous().view(-1, 1, l2.out_features)).view(l2.out_features, -1))
+    d_se = ops.small_linear(d_all, wcat_t, None)
+    d_emb = ops.silu_bwd(d_se, emb)
+    # time_embed.2: input hid = silu(hid_pre)
+    w0 = _cache(l0).get("w2d", prepare.linear_params(l0), lambda: prepare.effective_linear_weight(l0).view(l0.out_features, -1))
+    hid_pre = ops.small_linear(t_emb, w0, f32(l0.bias))
+    _small_lora_grads(l2, hid_pre, d_emb, G, silu_x=True)
+    w2t = _cache(l2).get("w2dT", prepare.linear_params(l2), lambda: prepare.weight_T(
+        prepare.effective_linear_weight(l2)).view(l2.in_features, l2.out_features))
+    d_hid = ops.small_linear(d_emb, w2t, None)
+    d_hid_pre = ops.silu_bwd(d_hid, hid_pre)
+    _small_lora_grads(l0, t_emb, d_hid_pre, G)
 
 
 # ------------------------------------------------------------------------------------------------ networks
@@ -441,7 +545,13 @@ def zero_conv_bwd(seq, h, d_out, G, upstream):
     return nchw_view(ops.gemm(dp, wt, residual=up))
 
 
-def controlnet_bwd(cn, saved, d_outs, G):
+STAGE_AFTER_BLOCK = {9: "ib9", 6: "ib6", 3: "ib3"}  # backward stages that close a gradient bucket (besides "middle")
+
+
+def controlnet_bwd(cn, saved, d_outs, G, on_stage=None):
+    """Backward through the ControlNet, last block first.  `on_stage(name)` fires when every gradient of a bucket is final
+    ("middle": middle_block.*; "ib9"/"ib6"/"ib3": input_blocks 9-11 / 6-8 / 3-5) so the trainer can start that bucket's
+    all-reduce while the remaining blocks are still being differentiated."""
     from ldm.modules.diffusionmodules.openaimodel import ResBlock
     emb = saved["emb"]
     bsz = emb.raw.shape[0]
@@ -454,12 +564,16 @@ def controlnet_bwd(cn, saved, d_outs, G):
     tapes, hs = saved["tapes"], saved["hs"]
     d_h = zero_conv_bwd(cn.middle_block_out, hs[-1], d_outs[-1], G, None)
     d_h = seq_bwd(tapes[-1], d_h, G, emb_grads)
+    if on_stage is not None:
+        on_stage("middle")
     for i in range(len(cn.input_blocks) - 1, -1, -1):
         d_h = zero_conv_bwd(cn.zero_convs[i], hs[i], d_outs[i], G, d_h)
         d_h = seq_bwd(tapes[i], d_h, G, emb_grads)
+        if on_stage is not None and i in STAGE_AFTER_BLOCK:
+            on_stage(STAGE_AFTER_BLOCK[i])
     from ldm.modules.diffusionmodules.util import timestep_embedding
     t_emb = timestep_embedding(saved["t"], cn.model_channels)
-    emb_mlp_backward(cn, t_emb, emb.raw, emb_grads, G)
+    emb_mlp_backward(cn, t_emb, emb.raw, d_all, emb_grads, G)
 
 
 def unet_fwd(unet, x, t, ctx, control, scales, only_mid_control=False):
@@ -578,7 +692,7 @@ class FinetuneTrainer:
             d_ctrl = unet_bwd(self.unet, un_saved, d_eps)
             if m.only_mid_control:
                 d_ctrl = [d if d is not None else torch.zeros_like(c) for d, c in zip(d_ctrl, control)]
-            controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G)
+            controlnet_bwd(self.cn, cn_saved, d_ctrl, self.G, on_stage=getattr(self, "_on_stage", None))
         finally:
             ops.stats_arena_end(x0.device)
         self.last_eps = eps
@@ -589,12 +703,43 @@ class FinetuneTrainer:
         inv = 1.0 / self._scale_used
         return {n: g * inv for n, g in self.G.named_grads().items()}
 
-    def reduce_gradients(self):
-        """The path's single exchange step: ONE all-reduce (SUM) of the flat trainable-gradient buffer (36.9 M fp32
-        elements for rank 128 = 148 MB; the reference's DDP reduces ~10x more).  The 1/world factor is
-        folded into the AdamW kernel."""
+    # -- the exchange step: all-reduce (SUM) of the flat trainable-gradient buffer (36.9 M fp32 elements for rank 128 =
+    # 148 MB; the reference's DDP reduces ~10x more), split into buckets that follow the backward's order so
+    # all but the last one overlap the remaining ControlNet backward.  1/world is folded into the AdamW kernel.
+    def gradient_buckets(self):
+        """{stage: [(offset, numel)]}: contiguous flat-buffer ranges whose gradients are final when the backward reaches
+        the stage; "final" is the rest (input_blocks.0-2, zero-convs, time-embedding MLP, middle_block_out)."""
+        stage_of = lambda n: ("middle" if n.startswith("middle_block.") else
+                              next((st for b0, st in ((9, "ib9"), (6, "ib6"), (3, "ib3"))
+                                    if n.startswith("input_blocks.") and b0 <= int(n.split(".")[1]) < b0 + 3), "final"))
+        buckets = {k: [] for k in ("middle", "ib9", "ib6", "ib3", "final")}
+        for name in self.G.names:
+            off, n = self.G.offsets[name]
+            r = buckets[stage_of(name)]
+            if r and r[-1][0] + r[-1][1] == off:
+                r[-1] = (r[-1][0], r[-1][1] + n)
+            else:
+                r.append((off, n))
+        return buckets
+
+    def _reduce_ranges(self, ranges):
+        """all-reduce `ranges` on the communication stream once everything enqueued so far on the compute stream is done"""
+        if self.world <= 1 or not ranges:
+            return
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        self._comm.wait_event(ev)
+        with torch.cuda.stream(self._comm):
+            for off, n in ranges:
+                torch.distributed.all_reduce(self.G.flat_g[off:off + n], group=self.pg)
+
+    def reduce_gradients(self, ranges=None):
+        """Un-overlapped form (also what the CPU/gloo test drives): one all-reduce per range, whole buffer by default."""
         if self.world > 1:
-            torch.distributed.all_reduce(self.G.flat_g, group=self.pg)
+            for off, n in (ranges or [(0, self.G.numel)]):
+                torch.distributed.all_reduce(self.G.flat_g[off:off + n], group=self.pg)
 
     # -- CUDA-graph replay of forward + backward (≈3 000 launches per step; Python cannot enqueue them fast enough)
     def capture(self, x0, hint_latent, context, t, noise, warmup=2):
@@ -610,6 +755,35 @@ class FinetuneTrainer:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         prepare.bump_train_version()  # force the trainable-weight preparation into the captured region
+        self._segments = None
+        if self.world > 1 and getattr(self, "overlap_allreduce", True):
+            # one graph per gradient bucket, sharing a memory pool: replay k, start bucket k's all-reduce on the
+            # communication stream, replay k+1 ...  (NCCL stays outside the captures)
+            buckets = self.gradient_buckets()
+            segs, state = [], {}
+            stream = torch.cuda.Stream()
+            stream.wait_stream(cur)
+            with torch.cuda.stream(stream):
+                state["g"] = torch.cuda.CUDAGraph()
+                state["g"].capture_begin()
+
+                def on_stage(name):
+                    state["g"].capture_end()
+                    segs.append((state["g"], buckets[name]))
+                    state["g"] = torch.cuda.CUDAGraph()
+                    state["g"].capture_begin(pool=segs[0][0].pool())
+
+                self._on_stage = on_stage
+                try:
+                    self._static_loss = self.loss_and_grads(*self._static)
+                finally:
+                    self._on_stage = None
+                state["g"].capture_end()
+                segs.append((state["g"], buckets["final"]))
+            cur.wait_stream(stream)
+            self._segments = segs
+            self._graph = segs[0][0]
+            return self
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._static_loss = self.loss_and_grads(*self._static)
@@ -619,15 +793,34 @@ class FinetuneTrainer:
         for dst, src in zip(self._static, (x0, hint_latent, context, t, noise)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        self._graph.replay()
+        if self._segments:
+            for g, ranges in self._segments:
+                g.replay()
+                self._reduce_ranges(ranges)
+        else:
+            self._graph.replay()
         return self._static_loss
 
     def step(self, x0, hint_latent, context, t, noise):
+        overlapped = False
         if getattr(self, "_graph", None) is not None:
             loss = self.loss_and_grads_graphed(x0, hint_latent, context, t, noise)
+            overlapped = bool(self._segments)
+        elif self.world > 1 and getattr(self, "overlap_allreduce", True):
+            buckets = self.gradient_buckets()
+            self._on_stage = lambda name: self._reduce_ranges(buckets[name])
+            try:
+                loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
+            finally:
+                self._on_stage = None
+            self._reduce_ranges(buckets["final"])
+            overlapped = True
         else:
             loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
-        self.reduce_gradients()
+        if overlapped:
+            torch.cuda.current_stream().wait_stream(self._comm)  # every bucket reduced before the overflow check / AdamW
+        else:
+            self.reduce_gradients()
         ops.nonfinite_flag(self.G.flat_g, self.overflow_flag)  # after the all-reduce: every rank takes the same decision
         self.step_count += 1
         ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,
@@ -646,3 +839,157 @@ class FinetuneTrainer:
 
     def _overflowed(self):
         return bool(self.overflow_flag.item())
+
+
+
+# ------------------------------------------------------------------------------------------------ pretraining
+def pretrain_parameters(control_model):
+    """The pretrain optimizer's set: `list(control_model.parameters())` as the reference sees it in
+    configure_optimizers (cldm_ctrlora_pretrain.py:174-182), i.e. before any switch_lora: the ControlNet's own parameters in
+    module order, then every task's LoRA set under loras_dict.  (After a switch the attached set is ALSO reachable as
+    `<linear>.lora_layer.*`; those aliases are skipped so the order does not depend on the attached task.)"""
+    out, seen = [], set()
+    for n, p in control_model.named_parameters(remove_duplicate=False):
+        if ".lora_layer." in n or id(p) in seen:
+            continue
+        seen.add(id(p))
+        out.append((n, p))
+    return out
+
+
+def active_segments(layout, tasks_on_ranks):
+    """[(offset, numel, key)] of the flat buffer a step touches: the ControlNet's own parameters plus the LoRA sets of
+    the tasks any rank trained this step.  A set no rank used keeps `grad is None` in the reference (DDP with
+    find_unused_parameters leaves globally unused parameters untouched, and AdamW skips them -- no moment update, no
+    weight decay), so it is neither reduced nor stepped here."""
+    segs = [layout["base"] + ("base",)]
+    for task in sorted(set(tasks_on_ranks), key=layout["tasks"].index):
+        segs.append(layout["lora"][task] + (task,))
+    return segs
+
+
+class PretrainTrainer(FinetuneTrainer):
+    """Base-ControlNet pretraining step (configs ctrlora_pretrain_sd15_9tasks_rank128.yaml): every ControlNet parameter
+    and the mini-batch task's LoRA set are trained (cldm_ctrlora_pretrain.py:88-111,174-182); the task changes per
+    mini-batch (datasets/multi_task_scheduler.py, mirrored by ctrlora_b200.scheduler.TaskSchedule).  Also covers
+    ControlNetFinetune(ft_with_lora=False) (full-parameter finetuning, cldm_ctrlora_finetune.py:101-104)."""
+
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None,
+                 loss_scale=None, dynamic_loss_scale=True):
+        self.model = model
+        self.cn = model.control_model
+        self.unet = model.model.diffusion_model
+        self.tasks = list(getattr(self.cn, "tasks", []))
+        self.G = GradSink(self.cn, named=pretrain_parameters(self.cn))
+        names = self.G.names
+        first_lora = next((i for i, n in enumerate(names) if n.startswith("loras_dict.")), len(names))
+        base_end = self.G.offsets[names[first_lora]][0] if first_lora < len(names) else self.G.numel
+        self.layout = {"base": (0, base_end), "tasks": self.tasks, "lora": {}}
+        for task in self.tasks:
+            mine = [self.G.offsets[n] for n in names if n.startswith(f"loras_dict.{task}.")]
+            start = mine[0][0]
+            assert all(o == start + sum(m[1] for m in mine[:i]) for i, (o, _) in enumerate(mine)), "task set not contiguous"
+            self.layout["lora"][task] = (start, sum(m[1] for m in mine))
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        if self.world > 1:
+            torch.distributed.broadcast(self.G.flat_p, src=0, group=process_group)
+            prepare.bump_train_version()
+        self.step_count = 0
+        self.seg_steps = {}        # per-segment AdamW step counts (torch keeps `step` per parameter)
+        self.loss_scale, self.dynamic_loss_scale = loss_scale, dynamic_loss_scale
+        self.overflow_flag = torch.zeros(1, device=self.G.flat_p.device, dtype=torch.int32)
+        self.skipped_steps = 0
+        self._graphs, self._pool, self._static, self._static_loss = {}, None, None, {}
+        self.task = self.tasks[0] if self.tasks else None
+
+    def loss_and_grads(self, x0, hint_latent, context, t, noise, task=None):
+        if task is not None and self.tasks:
+            self.cn.switch_lora(task)
+            self.task = task
+        return super().loss_and_grads(x0, hint_latent, context, t, noise)
+
+    # -- one CUDA graph per task (the attached LoRA set is baked into the captured kernels' pointers); the graphs share one
+    # memory pool: only one of them is ever in flight
+    def capture(self, x0, hint_latent, context, t, noise, tasks=None, warmup=2):
+        if self._static is None:
+            self._static = [v.clone() for v in (x0, hint_latent, context, t, noise)]
+        for task in (tasks or self.tasks or [None]):
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self.loss_and_grads(*self._static, task=task)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            prepare.bump_train_version()
+            g = torch.cuda.CUDAGraph()
+            kw = {} if self._pool is None else {"pool": self._pool}
+            with torch.cuda.graph(g, **kw):
+                self._static_loss[task] = self.loss_and_grads(*self._static, task=task)
+            if self._pool is None:
+                self._pool = g.pool()
+            self._graphs[task] = (g, self._scale_used)
+        return self
+
+    def _tasks_on_ranks(self, task):
+        if self.world == 1 or not self.tasks:
+            return [task]
+        mine = torch.tensor([self.tasks.index(task)], device=self.G.flat_p.device, dtype=torch.int64)
+        allv = [torch.empty_like(mine) for _ in range(self.world)]
+        torch.distributed.all_gather(allv, mine, group=self.pg)
+        return [self.tasks[int(v.item())] for v in allv]
+
+    def segments_for(self, task):
+        return active_segments(self.layout, self._tasks_on_ranks(task)) if self.tasks else [(0, self.G.numel, "base")]
+
+    def reduce_gradients(self, segs=None):
+        """The exchange step: all-reduce (SUM) of the ControlNet segment and of every LoRA set some rank trained this step
+        (the reference's DDP reduces all 589 M elements every step; unused sets are all-zero there)."""
+        if self.world > 1:
+            for off, n, _ in (segs or [(0, self.G.numel, "all")]):
+                torch.distributed.all_reduce(self.G.flat_g[off:off + n], group=self.pg)
+
+    def step(self, x0, hint_latent, context, t, noise, task=None):
+        task = task if task is not None else self.task
+        if task in self._graphs:
+            for dst, src in zip(self._static, (x0, hint_latent, context, t, noise)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+            if self.tasks:
+                self.cn.switch_lora(task)  # host-side pointers follow the graph (weight caches are keyed on them)
+                self.task = task
+            g, self._scale_used = self._graphs[task]
+            g.replay()
+            loss = self._static_loss[task]
+        else:
+            loss = self.loss_and_grads(x0, hint_latent, context, t, noise, task=task)
+        segs = self.segments_for(task)
+        self.reduce_gradients(segs)
+        for off, n, _ in segs:
+            ops.nonfinite_flag(self.G.flat_g[off:off + n], self.overflow_flag)
+        self.step_count += 1
+        G = self.G
+        for off, n, key in segs:
+            k = self.seg_steps.get(key, 0) + 1
+            self.seg_steps[key] = k
+            ops.adamw_step(G.flat_p[off:off + n], G.flat_g[off:off + n], G.exp_avg[off:off + n], G.exp_avg_sq[off:off + n], k,
+                           lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
+                           grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag)
+        prepare.bump_train_version()
+        if self.dynamic_loss_scale and self._overflowed():
+            self.step_count -= 1
+            for _, _, key in segs:
+                self.seg_steps[key] -= 1
+            self.skipped_steps += 1
+            self.loss_scale = self._scale_used * 0.5
+            if self._graphs:
+                tasks = list(self._graphs)
+                self._graphs.clear()
+                self.capture(*self._static, tasks=tasks, warmup=1)
+        return loss

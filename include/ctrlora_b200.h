@@ -133,6 +133,17 @@ int ctrlora_small_linear(const float* x, int ldx, const void* w, const float* bi
 int ctrlora_upsample2x_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
 /* gather for Downsample's conv3x3 stride 2 pad 1 (openaimodel.py:148-159): dst [batch, h/2, w/2, 9, channels] */
 int ctrlora_im2col_s2_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
+/* same gather with the zero padding only on the right/bottom when pad_lo = 0: the first-stage VAE's
+ * F.pad(x, (0,1,0,1)) + Conv2d(stride 2, padding 0), ldm/modules/diffusionmodules/model.py:80-84 */
+int ctrlora_im2col_s2_pad_f16(const void* src, void* dst, int batch, int h, int w, int channels, int pad_lo, void* stream);
+/* softmax(scale * src) over rows, fp32 logits -> fp16 probabilities: the VAE's d = 512 single-head AttnBlock
+ * (model.py:179-203), whose logits come from ctrlora_gemm_f16 with out_f32 = 1 */
+int ctrlora_softmax_rows_f32_to_f16(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols,
+                                    float scale, void* stream);
+/* DiagonalGaussianDistribution.sample() / .mode() times scale_factor (ldm/modules/distributions/distributions.py:24-37,
+ * ldm/models/diffusion/ddpm.py get_first_stage_encoding): moments fp32 [batch, 2*z, hw]; noise NULL = mode. */
+int ctrlora_gaussian_sample(const float* moments, const float* noise, float* out, int batch, int z_channels, int hw, float scale,
+                            void* stream);
 /* weight preparation: fp32 [batch, rows, cols] -> fp16 [batch, cols, rows] */
 int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, long long batch, int rows, int cols, void* stream);
 
@@ -196,9 +207,13 @@ int ctrlora_image_colsum_f16(const void* x, long long ld, int images, int rows_p
  * dW[Cout, tap, Cin] of a 3x3 stride-1 conv = ctrlora_wgrad_tn_f16(dY [M, Cout], col [M, 9*Cin]) with
  * col[b, h, w, tap, c] = x[b, h+kh-1, w+kw-1, c]: */
 int ctrlora_im2col_3x3_f16(const void* src, void* dst, int batch, int h, int w, int channels, void* stream);
-/* out[n, k] = beta*out + alpha * sum_b dy[b, n] * x[b, k] (fp32; b = batch rows): time_embed / emb_layers weight gradients */
+/* out[n, k] = beta*out + alpha * sum_b dy[b, n] * f(x[b, k]) (fp32; b = batch rows; f = SiLU when silu_x): time_embed /
+ * emb_layers weight gradients */
 int ctrlora_outer_accum_f32(const float* dy, int lddy, const float* x, int ldx, float* out, long long ldo, int rows, int n, int k,
-                            float alpha, float beta, void* stream);
+                            float alpha, float beta, int silu_x, void* stream);
+/* dst[r, c] (+)= src[r, c], fp32, row strides lds / ldd */
+int ctrlora_copy2d_f32(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols, int accumulate,
+                       void* stream);
 /* out = d * silu'(x) (fp32): backward of the SiLU in the time-embedding MLP (openaimodel.py:526-531, :208-215) */
 int ctrlora_silu_bwd_f32(const float* d, const float* x, float* out, long long n, void* stream);
 /* fp32 [rows, cols] (row stride lds) -> dense fp16 [rows, cols] */

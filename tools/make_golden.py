@@ -358,11 +358,102 @@ def full_train(seed=0):
     print("wrote", out, os.path.getsize(out) // 1024, "KiB", "in", time.time() - t0, "s")
 
 
+def _vae_image(name, shape, seed):
+    """synthetic image in [-1, 1]: smooth-ish so that 512x512 inputs are not pure white noise"""
+    x = synth.synth_input(name, shape, seed)
+    x = torch.nn.functional.avg_pool2d(x, 3, stride=1, padding=1) * 2.0
+    return torch.tanh(x)
+
+
+def vae(seed=0, full=False):
+    """First-stage VAE (reference ldm/models/autoencoder.py:82-91, ldm/modules/diffusionmodules/model.py:452-654):
+    encode moments / mode and decode on the tiny config, and (--vae-full) on the SD VAE at 512x512, B = 1."""
+    ref_shims.install()
+    from omegaconf import OmegaConf
+    from ldm.util import instantiate_from_config
+    g = {"seed": seed}
+    if not full:
+        cfg = OmegaConf.load(os.path.join(GOLD, "tiny_finetune.yaml")).model.params.first_stage_config
+        B, R = 2, 32
+    else:
+        cfg = OmegaConf.load(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "ctrlora_finetune_sd15_rank128.yaml")).model.params.first_stage_config
+        B, R = 1, 512
+    torch.manual_seed(0)
+    m = instantiate_from_config(cfg).eval()
+    shapes = shapes_of(m)
+    m.load_state_dict(synth.synth_state_dict(shapes, seed, "first_stage_model."), strict=True)
+    g["shapes"], g["key_order"] = shapes, list(m.state_dict().keys())
+    img = _vae_image("vae_img", (B, 3, R, R), seed)
+    z = synth.synth_input("vae_z", (B, 4, R // 8 if full else R // 2, R // 8 if full else R // 2), seed)
+    t0 = time.time()
+    with torch.no_grad():
+        post = m.encode(img)
+        g["moments"] = post.parameters.clone()
+        g["mode"] = post.mode().clone()
+        torch.manual_seed(123)
+        g["sample_seed123"] = post.sample().clone()
+        print("encode", time.time() - t0, flush=True)
+        dec = m.decode(z)
+        print("decode", time.time() - t0, flush=True)
+    if full:  # keep the fixture small: a crop, a strided subsample and the norm of the 3 MB image
+        g["decode_crop"] = dec[:, :, 192:320, 192:320].clone()
+        g["decode_strided"] = dec[:, :, ::8, ::8].clone()
+        g["decode_norm"] = dec.norm().item()
+    else:
+        g["decode"] = dec.clone()
+        with torch.no_grad():
+            g["roundtrip"] = m.decode(post.mode()).clone()
+    out = os.path.join(GOLD, "sd_vae_golden.pt" if full else "tiny_vae_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
+def schedule():
+    """Task order produced by the reference's BatchSchedulerSampler for seeded np.random (tests/test_scheduler_cpu.py)."""
+    import json
+    sys.path.insert(0, ref_shims.REFERENCE_ROOT)
+    from datasets.multi_task_scheduler import BatchSchedulerSampler
+    from torch.utils.data import ConcatDataset, Dataset
+
+    class Fake(Dataset):
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            return i
+
+    cases = []
+    for seed, sizes, bs, shuffle in ((0, [40, 40, 40], 8, True), (1, [17, 64, 33, 50], 16, True), (2, [10] * 9, 4, True),
+                                     (3, [12, 30], 5, False)):
+        tasks = [f"task{i}" for i in range(len(sizes))]
+        ds = ConcatDataset([Fake(n) for n in sizes])
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        idx = list(BatchSchedulerSampler(ds, bs, distributed=False, shuffle=shuffle))
+        bounds = np.asarray(ds.cumulative_sizes)
+        per_batch = []
+        for b0 in range(0, len(idx), bs):
+            owners = {int(np.searchsorted(bounds, i, side="right")) for i in idx[b0:b0 + bs]}
+            assert len(owners) == 1  # one task per mini-batch
+            per_batch.append(tasks[owners.pop()])
+        cases.append({"seed": seed, "tasks": tasks, "largest": max(sizes), "batch_size": bs, "shuffle": shuffle,
+                      "task_per_batch": per_batch})
+    out = os.path.join(GOLD, "task_schedule_golden.json")
+    json.dump({"cases": cases}, open(out, "w"), indent=1)
+    print("wrote", out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--full-train", action="store_true")
+    ap.add_argument("--schedule", action="store_true")
+    ap.add_argument("--vae", action="store_true")
+    ap.add_argument("--vae-full", action="store_true")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if a.full:
@@ -371,5 +462,11 @@ if __name__ == "__main__":
         variants()
     elif a.full_train:
         full_train()
+    elif a.schedule:
+        schedule()
+    elif a.vae:
+        vae()
+    elif a.vae_full:
+        vae(full=True)
     else:
         tiny()
