@@ -97,6 +97,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def ncu_gemm_traffic():
+    """DRAM bytes of the GEMM family per DDIM step from the committed ncu launch list of this same workload
+    (profiles/r2_shares_ddim_step.json, written by tools/launch_shares.py from `ncu --metrics ...dram__bytes...` over
+    tools/profile_step.py); None when the capture is absent."""
+    path = os.path.join(ROOT, "profiles", "r2_shares_ddim_step.json")
+    try:
+        fam = json.load(open(path))["families"]["gemm_tcgen05"]
+        return fam["dram_bytes"] if fam["dram_bytes"] > 0 else None, os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -147,37 +159,117 @@ def cpu_state_dict(seed=0):
     return sd
 
 
+def pick_cpu_threads():
+    """Thread count for the CPU arm, chosen by a ~2 s probe on this box (conv + GEMM of the path's shapes at 16 / 32 / 64 /
+    all cores): torch's intra-op scaling on this model is far from linear, and the best count differs between box classes."""
+    import torch.nn.functional as F
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (16, 32, 64, cores) if c <= cores} or {cores})
+    x = torch.randn(1, 320, 64, 64)
+    w = torch.randn(320, 320, 3, 3)
+    a, b = torch.randn(4096, 320), torch.randn(320, 1280)
+    best, best_t, probe = cands[0], None, {}
+    for c in cands:
+        torch.set_num_threads(c)
+        for _ in range(2):
+            F.conv2d(x, w, padding=1); a @ b
+        t0 = time.perf_counter()
+        for _ in range(6):
+            F.conv2d(x, w, padding=1); a @ b
+        dt = (time.perf_counter() - t0) / 6
+        probe[c] = round(dt * 1e3, 3)
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best, cores, probe
+
+
+def cpu_reference_step(model_state, seed=1):
+    """One DDIM step of the workload the way the reference executes it (cldm/ddim_hacked.py:188-192): apply_model on the
+    conditional batch of 4, then on the unconditional batch of 4 -- 8 image passes, nothing extrapolated."""
+    from oracle import ctrlora_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(BATCH, 4, LATENT, LATENT, generator=g)
+    hint = torch.randn(BATCH, 4, LATENT, LATENT, generator=g)
+    ctx = torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=g)
+    uc = torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=g)
+    t = torch.full((BATCH,), 501, dtype=torch.long)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        e_c = O.apply_model(model_state, x, t, ctx, hint, 8, 320)
+        e_u = O.apply_model(model_state, x, t, uc, hint, 8, 320)
+        tab = O.ddim_tables(O.register_schedule(), 50, 0.0)
+        O.ddim_update(x, O.cfg_combine(e_c, e_u, CFG_SCALE), tab, 25)
+    return time.perf_counter() - t0
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference is a Python
-    tree that cannot travel to the GPU box), all host threads, same config/metric/unit.  One 'step' of this arm is a
-    bounded sample of the DDIM step: ONE of its 8 image passes (apply_model at batch 1)."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port; /root/reference is a Python tree that
+    cannot travel to the GPU box), same config / metric / unit.  One 'step' = one full DDIM step of the workload (two
+    batch-4 apply_model passes + the update), not an extrapolated sample; the step count is cut to fit a few minutes."""
     if rank != 0:
         return
-    threads = min(os.cpu_count() or 1, 32)  # torch's intra-op scaling on this model collapses beyond ~32 threads
+    threads, cores, probe = pick_cpu_threads()
     sd = cpu_state_dict()
-    times = []
-    budget_s = 240.0
-    t_first = cpu_reference_pass(sd, threads)  # warm-up 1 (also sizes the run)
-    warm = max(0, args.warmup - 1)
-    steps = args.steps
-    if t_first * (warm + steps) > budget_s:  # keep the whole arm within a few minutes
-        warm = 0
-        steps = max(1, int(budget_s / t_first) - 1)
-    for _ in range(warm):
-        cpu_reference_pass(sd, threads)
-    for _ in range(steps):
-        times.append(cpu_reference_pass(sd, threads))
-    t_pass = sum(times) / len(times)
-    passes_per_step = 2 * BATCH
-    value = 1.0 / (t_pass * passes_per_step)
+    budget_s = 300.0
+    t_first = cpu_reference_step(sd)  # warm-up (also sizes the run)
+    steps = max(3, min(args.steps, int(budget_s / t_first) - 1))
+    times = sorted(cpu_reference_step(sd) for _ in range(steps))
+    t_step = times[len(times) // 2]  # median: the arm has to be reproducible, a single stalled step must not move it
+    value = 1.0 / t_step
     line = {"impl": "reference", "metric": "ddim_steps_per_sec", "value": value, "unit": "steps/s (batch 4, CFG)",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": t_pass * passes_per_step * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": t_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "steps/s (batch 4, CFG)", "cores": threads, "kind": "port",
-                             "sample": f"{steps} x one apply_model at batch 1 (1/8 of a DDIM step each), "
-                                       f"{t_pass:.2f} s per pass, extrapolated x8"},
+            "cpu_baseline": {"value": value, "unit": "steps/s (batch 4, CFG)", "cores": threads, "host_cores": cores,
+                             "kind": "port", "thread_probe_ms": probe,
+                             "sample": f"{steps} full DDIM steps (2 x apply_model at batch 4 + update), median {t_step:.2f} s, "
+                                       f"min {times[0]:.2f} s, max {times[-1]:.2f} s"},
             "e2e": {"value": value, "unit": "steps/s (batch 4, CFG)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_reference_gpu(args, rank, world):
+    """--impl reference-gpu: the library comparator SURVEY.md §8(d) asks for -- the reference's algorithm (oracle port: plain
+    torch ops = cuDNN / cuBLAS / ATen eager, N x N attention matrix materialised like the reference) on the SAME B200, in
+    fp32 and under bf16 autocast.  Two sequential batch-4 passes per step like the reference's sampler.  Not a product path."""
+    if rank != 0:
+        return
+    from oracle import ctrlora_oracle as O
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in cpu_state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(BATCH, 4, LATENT, LATENT, generator=g).to(dev)
+    hint = torch.randn(BATCH, 4, LATENT, LATENT, generator=g).to(dev)
+    ctx = torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=g).to(dev)
+    uc = torch.randn(BATCH, CTX_TOKENS, CTX_DIM, generator=g).to(dev)
+    t = torch.full((BATCH,), 501, dtype=torch.long, device=dev)
+    tab = O.ddim_tables(O.register_schedule(), 50, 0.0)
+
+    def step():
+        e_c = O.apply_model(sd, x, t, ctx, hint, 8, 320)
+        e_u = O.apply_model(sd, x, t, uc, hint, 8, 320)
+        return O.ddim_update(x, O.cfg_combine(e_c.float(), e_u.float(), CFG_SCALE), tab, 25)
+
+    res = {}
+    for name, ctxmgr in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with torch.no_grad(), ctxmgr:
+            for _ in range(max(3, args.warmup)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        res[name] = {"ms_per_step": ms, "steps_per_sec": 1e3 / ms}
+    line = {"impl": "reference-gpu", "metric": "ddim_steps_per_sec", "value": res["fp32"]["steps_per_sec"],
+            "unit": "steps/s (batch 4, CFG)", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": res["fp32"]["ms_per_step"], "higher_is_better": True, "dtype": "f32 (torch eager, TF32 off)",
+            "data": "synthetic", "config": workload_config(1), "variants": res,
+            "note": "oracle port on cuda:0 = the reference's op sequence through cuDNN/cuBLAS/ATen; comparator only"}
     print(json.dumps(line))
 
 
@@ -350,7 +442,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lora-rank", type=int, default=128, choices=[32, 64, 128, 256, 512],
                     help="training workload only: BASELINE.json configs[4] rank sweep (default: the rank-128 headline)")
@@ -363,6 +455,9 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.impl == "reference-gpu":
+        run_reference_gpu(args, rank, world)
         return
 
     import torch.distributed as dist
@@ -505,20 +600,25 @@ def main():
                 "roofline": {"kernel": "gemm_tcgen05_kernel (all convs + linears of one step, replayed back to back from a CUDA graph)",
                              "bound": "tensor",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                             "peak_source": peak_src + ", sustained bf16/fp16 dense", "traffic": None,
+                             "peak_source": peak_src + ", sustained bf16/fp16 dense", "traffic": ncu_gemm_traffic()[0],
+                             "traffic_unit": "DRAM bytes per step, all GEMM launches (ncu dram__bytes_read+write)",
+                             "traffic_source": ncu_gemm_traffic()[1],
                              "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,
                              "share_of_step": gemm_stats["ms"] / (ms_dev / args.steps)}}
         if train_result is not None:
             line["train"] = train_result
+            # BASELINE.json's second headline metric, lifted to the top level so that the scaling record keeps it
+            line["train_images_per_sec"] = train_result["value"]
+            line["train_ms_per_step"] = train_result["ms_per_step"]
+            line["train_e2e_images_per_sec"] = train_result["e2e"]["value"]
         if not args.no_cpu_baseline:
-            threads = min(os.cpu_count() or 1, 32)  # torch's intra-op scaling on this model collapses beyond ~32 threads
+            threads, cores, probe = pick_cpu_threads()
             sd = cpu_state_dict()
-            cpu_reference_pass(sd, threads)
-            tp = cpu_reference_pass(sd, threads)
-            v = 1.0 / (tp * 2 * BATCH)
-            line["cpu_baseline"] = {"value": v, "unit": "steps/s (batch 4, CFG)", "cores": threads, "kind": "port",
-                                    "sample": f"one apply_model at batch 1 (1/8 of a DDIM step) after one warm-up, "
-                                              f"{tp:.2f} s, extrapolated x8"}
+            cpu_reference_pass(sd, threads)  # warm-up (one batch-1 pass)
+            tp = cpu_reference_step(sd)
+            line["cpu_baseline"] = {"value": 1.0 / tp, "unit": "steps/s (batch 4, CFG)", "cores": threads, "host_cores": cores,
+                                    "kind": "port", "thread_probe_ms": probe,
+                                    "sample": f"ONE full DDIM step (2 x apply_model at batch 4 + update) after a warm-up pass, {tp:.2f} s"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -37,6 +37,7 @@ class GroupNormArgs(C.Structure):
         ("batch", c_int), ("hw", c_int), ("groups", c_int),
         ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("silu", c_int),
         ("y", c_void_p), ("raw_out", c_void_p), ("stats_ws", c_void_p), ("stats_prezeroed", c_int),
+        ("partial_ws", c_void_p), ("partial_ws_floats", c_ll), ("partial_counters", c_void_p), ("partial_counters_len", c_int),
     ]
 
 

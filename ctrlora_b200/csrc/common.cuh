@@ -177,6 +177,30 @@ __device__ __host__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int fm
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// cluster launch that also chains programmatically (PDL) onto its predecessor in the stream
+template <typename... KArgs>
+inline cudaError_t launch_cluster_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      unsigned cluster_x, KArgs... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_x;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    const char* e = getenv("CTRLORA_PDL");
+    cfg.numAttrs = (e && e[0] == '0') ? 1 : 2;
+    void* ptrs[] = {(void*)&args...};
+    return cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), ptrs);
+}
+
 template <typename... KArgs>
 inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                   unsigned cluster_x, KArgs... args) {

@@ -304,13 +304,16 @@ extern "C" int ctrlora_timestep_embedding(const long long* t, const float* freqs
     return LAUNCH_OK();
 }
 
-// Same contract, for rows * K <= 40960 (e.g. 32 rows of 1280): the block stages act_in(x) ([rows][K] fp32) in shared memory once and its 8
-// warps then sweep SL_FPB output features.  The first version re-evaluated SiLU(emb) for every output feature (206 M
-// evaluations per UNet call -- MUFU-bound at ~65 us); now it is 10 240 per block.
-constexpr int SL_FPB = 64;
+// Same contract, for rows * K <= 40960 (e.g. 32 rows of 1280): the block stages act_in(x) ([rows][K] fp32) in shared memory once
+// (the first version re-evaluated SiLU(emb) for every output feature: 206 M evaluations per UNet call, MUFU-bound), then every
+// warp sweeps F output features AT A TIME against it: a lane owns 4 consecutive k per 128-wide chunk, so the activation reads
+// are conflict-free 16-byte shared loads shared by the F features (round 1 read shared memory once per feature with a 2-way
+// bank conflict and ran at ~0.4 TB/s of weight traffic), and the F weight rows are F independent 8-byte global loads per chunk.
+// Features per block follow N so that small layers (time_embed: N = 1280) still fill the machine.
+template <int F>
 __global__ void __launch_bounds__(256)
 small_linear_staged_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ w, const float* __restrict__ bias,
-                           float* __restrict__ y, int ldy, int rows, int N, int K, int silu_in, int silu_out) {
+                           float* __restrict__ y, int ldy, int rows, int N, int K, int silu_in, int silu_out, int groups_per_warp) {
     extern __shared__ float sx[];  // [rows][K]
     for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
         const int r = i / K, k = i - r * K;
@@ -319,50 +322,61 @@ small_linear_staged_kernel(const float* __restrict__ x, int ldx, const __half* _
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < SL_FPB; j += 8) {
-        const int n = blockIdx.x * SL_FPB + j;
-        if (n >= N) break;
-        for (int r0 = 0; r0 < rows; r0 += 8) {  // 8 rows per pass over the feature's weights (second pass hits L1)
-            float acc[8];
+    const int chunks = (K + 127) >> 7;
+    for (int gidx = 0; gidx < groups_per_warp; ++gidx) {
+        const int n0 = ((blockIdx.x * 8 + warp) * groups_per_warp + gidx) * F;
+        if (n0 >= N) break;
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+            float acc[F][8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-            // the whole weight row of this feature in flight at once (K <= 2048: eight 16-byte loads per lane)
-            uint4 uw[8];
+            for (int f = 0; f < F; ++f)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int k = lane * 8 + c * 256;
-                uw[c] = k < K ? __ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k)) : make_uint4(0u, 0u, 0u, 0u);
-            }
+                for (int r = 0; r < 8; ++r) acc[f][r] = 0.f;
+            for (int c = 0; c < chunks; ++c) {
+                const int k = (c << 7) + lane * 4;
+                const bool kin = k < K;  // K % 8 == 0 and k % 4 == 0: a 4-vector is either inside or outside
+                uint2 uw[F];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int k = lane * 8 + c * 256;
-                if (k < K) {
-                    const __half2* h = reinterpret_cast<const __half2*>(&uw[c]);
-                    float wv[8];
+                for (int f = 0; f < F; ++f)
+                    uw[f] = (kin && n0 + f < N) ? __ldg(reinterpret_cast<const uint2*>(w + static_cast<long long>(n0 + f) * K + k))
+                                                : make_uint2(0u, 0u);
+                if (!kin) continue;
+                float wv[F][4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); wv[2 * e] = f.x; wv[2 * e + 1] = f.y; }
+                for (int f = 0; f < F; ++f) {
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&uw[f].x));
+                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&uw[f].y));
+                    wv[f][0] = a.x; wv[f][1] = a.y; wv[f][2] = b.x; wv[f][3] = b.y;
+                }
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        if (r0 + r < rows) {
-                            const float4 a = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k);
-                            const float4 b = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k + 4);
-                            acc[r] += a.x * wv[0] + a.y * wv[1] + a.z * wv[2] + a.w * wv[3] + b.x * wv[4] + b.y * wv[5] + b.z * wv[6] + b.w * wv[7];
-                        }
+                for (int r = 0; r < 8; ++r) {
+                    if (r0 + r < rows) {
+                        const float4 xv = *reinterpret_cast<const float4*>(sx + (r0 + r) * K + k);
+#pragma unroll
+                        for (int f = 0; f < F; ++f)
+                            acc[f][r] += xv.x * wv[f][0] + xv.y * wv[f][1] + xv.z * wv[f][2] + xv.w * wv[f][3];
                     }
                 }
             }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int f = 0; f < F; ++f)
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-            }
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[f][r] += __shfl_xor_sync(0xffffffffu, acc[f][r], o);
             if (lane == 0) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (r0 + r < rows) {
-                        float v = acc[r] + (bias ? bias[n] : 0.f);
-                        if (silu_out) v = silu_f(v);
-                        y[static_cast<long long>(r0 + r) * ldy + n] = v;
+                for (int f = 0; f < F; ++f) {
+                    if (n0 + f < N) {
+                        const float bv = bias ? bias[n0 + f] : 0.f;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            if (r0 + r < rows) {
+                                float v = acc[f][r] + bv;
+                                if (silu_out) v = silu_f(v);
+                                y[static_cast<long long>(r0 + r) * ldy + n0 + f] = v;
+                            }
+                        }
                     }
                 }
             }
@@ -377,12 +391,19 @@ extern "C" int ctrlora_small_linear(const float* x, int ldx, const void* w, cons
         const size_t sm = static_cast<size_t>(rows) * k * sizeof(float);
         static bool attr = false;
         if (!attr) {
-            if (cudaFuncSetAttribute(small_linear_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960 * 4) != cudaSuccess)
+            if (cudaFuncSetAttribute(small_linear_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960 * 4) != cudaSuccess ||
+                cudaFuncSetAttribute(small_linear_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960 * 4) != cudaSuccess)
                 return CTRLORA_ERR_CUDA;
             attr = true;
         }
-        small_linear_staged_kernel<<<(n + SL_FPB - 1) / SL_FPB, 256, sm, STREAM(stream)>>>(
-            x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy, rows, n, k, silu_in, silu_out);
+        const __half* wp = reinterpret_cast<const __half*>(w);
+        if (n >= 4096) {  // 4 features per warp pass, 2 passes: 64 features per block (e.g. 20 160 emb_layers rows -> 315 blocks)
+            small_linear_staged_kernel<4><<<(n + 63) / 64, 256, sm, STREAM(stream)>>>(x, ldx, wp, bias, y, ldy, rows, n, k,
+                                                                                     silu_in, silu_out, 2);
+        } else {          // one feature per warp: 8 per block (time_embed N = 1280 -> 160 blocks)
+            small_linear_staged_kernel<1><<<(n + 7) / 8, 256, sm, STREAM(stream)>>>(x, ldx, wp, bias, y, ldy, rows, n, k, silu_in,
+                                                                                   silu_out, 1);
+        }
         return LAUNCH_OK();
     }
     small_linear_kernel<<<(n + 7) / 8, 256, 0, STREAM(stream)>>>(x, ldx, reinterpret_cast<const __half*>(w), bias, y, ldy,

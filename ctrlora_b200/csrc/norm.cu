@@ -84,6 +84,82 @@ gn_stats_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __
     }
 }
 
+// Deterministic statistics (used whenever the caller provides a partial workspace): per-thread partials are reduced through
+// shared memory in a fixed order, every block stores its per-group partial {sum, sumsq} (no atomics), and the LAST block of
+// an image to arrive (one self-cleaning counter per image) adds the partials up in block order and writes the totals.
+__global__ void __launch_bounds__(512)
+gn_stats_det_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, float* __restrict__ stats, float* __restrict__ partial,
+                    unsigned int* __restrict__ counters) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm[];  // [lanes][2][C] scratch, then [2][C] channel sums
+    __shared__ int is_last;
+    const int b = blockIdx.y;
+    const int vecs = C >> 3;
+    const int lanes = blockDim.x / vecs;  // blockDim.x == vecs * lanes exactly
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    float* csum = sm + static_cast<size_t>(lanes) * 2 * C;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    float a[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = 0.f; q[e] = 0.f; }
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(s, static_cast<long long>(b) * HW + p + u * lanes, vec * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] += v[u][e]; q[e] += v[u][e] * v[u][e]; }
+        }
+    }
+    for (; p < p1; p += lanes) {
+        float v[8];
+        load8(s, static_cast<long long>(b) * HW + p, vec * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += v[e]; q[e] += v[e] * v[e]; }
+    }
+    float* sp = sm + static_cast<size_t>(pl) * 2 * C + vec * 8;
+    *reinterpret_cast<float4*>(sp) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(sp + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    *reinterpret_cast<float4*>(sp + C) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(sp + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += sm[static_cast<size_t>(l) * 2 * C + i];
+        csum[i] = t;
+    }
+    __syncthreads();
+    const int cpg = C / groups;
+    const int nblk = gridDim.x;
+    float* mine = partial + (static_cast<size_t>(b) * nblk + blockIdx.x) * groups * 2;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += csum[c]; sq += csum[C + c]; }
+        mine[2 * g] = su;
+        mine[2 * g + 1] = sq;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&counters[b], 1u);
+        is_last = (old == static_cast<unsigned int>(nblk - 1));
+        if (is_last) counters[b] = 0;  // self-cleaning: ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {
+        float t = 0.f;
+        const float* src = partial + static_cast<size_t>(b) * nblk * groups * 2 + i;
+        for (int k = 0; k < nblk; ++k) t += __ldcg(src + static_cast<size_t>(k) * groups * 2);  // block order: fixed
+        stats[b * groups * 2 + i] = t;
+    }
+}
+
 __global__ void __launch_bounds__(512, 2)  // <= 64 registers: four 240..256-thread blocks per SM, the whole grid in one wave
 gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
@@ -141,6 +217,190 @@ gn_apply_kernel(GnSrc s, int C, int HW, int groups, int pix_per_block, const flo
         float v[8];
         load8(s, static_cast<long long>(b) * HW + p, vec * 8, v);
         emit(static_cast<long long>(b) * HW + p, v);
+    }
+}
+
+// ---- single-pass GroupNorm on a thread-block CLUSTER: the image's activations are read from HBM/L2 ONCE, parked in the
+// shared memory of the `cs` CTAs of a cluster (one cluster per image, each CTA holds HW/cs pixels x C channels, <= 200 KB),
+// the per-group {sum, sumsq} partials are exchanged through distributed shared memory, and every CTA normalises its own
+// slice out of shared memory.  Replaces the two-pass pair (gn_stats_kernel + gn_apply_kernel: two launches, the tensor read
+// twice) wherever the slice fits -- every GroupNorm of the 512x512 path except the decoder's widest concat inputs.
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t cta_rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(cta_rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// BULK: the slice of this CTA is one contiguous block of global memory (single source, no addend, dense rows): it is
+// brought in by the TMA engine (cp.async.bulk, 32 KiB pieces on one mbarrier) with no registers in the way; otherwise (the
+// UNet decoder's `cat([h, hs.pop() + control.pop()])` inputs) the threads gather it with 16-byte loads, four in flight each.
+// MODE 2 (no tile): slices too large for shared memory (the decoder's widest concat inputs) keep the cluster-wide statistics
+// exchange but re-read their input (from L2) for the normalisation pass -- still one launch, still deterministic.
+// Determinism: no atomics anywhere -- per-thread partials go through a shared scratch array and are summed in a fixed order,
+// CTA partials are summed in rank order -- so a forward pass is bit-reproducible.  (With fp16 storage this matters more than
+// it sounds: a 1e-7 perturbation of one statistic flips a few fp16 roundings, and every following rounding stage amplifies
+// the difference towards the rounding-noise level itself; the two-pass kernels' fp32 atomics made two identical SD1.5
+// passes differ by 1.6e-3, tools/debug_determinism.py.)
+template <int MODE>  // 0: register-gathered tile, 1: TMA bulk-staged tile, 2: no tile
+__global__ void __launch_bounds__(512, 1)
+gn_cluster_kernel(GnSrc s, int C, int HW, int groups, int ppc, int cs, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, int silu, __half* __restrict__ y, __half* __restrict__ raw,
+                  float* __restrict__ stats_out) {
+    constexpr bool BULK = MODE == 1;
+    constexpr bool TILE = MODE != 2;
+    pdl_launch_dependents();
+    extern __shared__ __align__(128) uint8_t gsm[];
+    __half* tile = reinterpret_cast<__half*>(gsm);                                    // [ppc][C] (absent in MODE 2)
+    float* scratch = reinterpret_cast<float*>(gsm + (TILE ? static_cast<size_t>(ppc) * C * 2 : 0));  // [lanes][2][C]
+    float* csum = scratch + static_cast<size_t>(blockDim.x / (C >> 3)) * 2 * C;      // [2][C]: per-channel sum, sumsq
+    float* part = csum + 2 * C;                                                       // [groups][2]: this CTA's group partials
+    float* mr = part + 2 * groups;                                                    // [groups][2]: mean, rstd
+    uint64_t* bar = reinterpret_cast<uint64_t*>(mr + 2 * groups);
+    const int b = blockIdx.y;
+    const uint32_t rank = cluster_ctarank();
+    const int vecs = C >> 3;
+    const int lanes = blockDim.x / vecs;
+    const int vec = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+    const int p0 = static_cast<int>(rank) * ppc, p1 = min(HW, p0 + ppc);
+    const int npix = max(p1 - p0, 0);
+    if (BULK && threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    pdl_wait();
+    float a[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] = 0.f; q[e] = 0.f; }
+    if (BULK) {
+        const uint32_t total = static_cast<uint32_t>(npix) * C * 2;  // multiple of 16
+        if (threadIdx.x == 0 && total > 0) {
+            mbar_expect_tx(bar, total);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(s.x1 + (static_cast<long long>(b) * HW + p0) * C);
+            for (uint32_t off = 0; off < total; off += 32768u)
+                bulk_g2s(gsm + off, src + off, min(32768u, total - off), bar);
+        }
+        if (total > 0) mbar_wait(bar, 0);
+        if (pl < lanes) {
+            for (int p = pl; p < npix; p += lanes) {
+                const uint4 w = *reinterpret_cast<const uint4*>(tile + static_cast<size_t>(p) * C + vec * 8);
+                const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h[e]);
+                    a[2 * e] += f.x; q[2 * e] += f.x * f.x;
+                    a[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+                }
+            }
+        }
+    } else if (pl < lanes) {
+        int p = pl;
+        for (; p + 3 * lanes < npix; p += 4 * lanes) {  // four 16-byte loads (eight with an addend) in flight per thread
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8(s, static_cast<long long>(b) * HW + p0 + p + u * lanes, vec * 8, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint4 w;
+                __half2* h = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[u][2 * e], v[u][2 * e + 1]);
+                if (TILE) *reinterpret_cast<uint4*>(tile + static_cast<size_t>(p + u * lanes) * C + vec * 8) = w;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { a[e] += v[u][e]; q[e] += v[u][e] * v[u][e]; }
+            }
+        }
+        for (; p < npix; p += lanes) {
+            float v[8];
+            load8(s, static_cast<long long>(b) * HW + p0 + p, vec * 8, v);
+            uint4 w;
+            __half2* h = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            if (TILE) *reinterpret_cast<uint4*>(tile + static_cast<size_t>(p) * C + vec * 8) = w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] += v[e]; q[e] += v[e] * v[e]; }
+        }
+    }
+    if (pl < lanes) {  // fixed-order reduction over the pixel lanes (no atomics: bit-reproducible statistics)
+        float* sp = scratch + static_cast<size_t>(pl) * 2 * C + vec * 8;
+        *reinterpret_cast<float4*>(sp) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(sp + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        *reinterpret_cast<float4*>(sp + C) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4*>(sp + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += scratch[static_cast<size_t>(l) * 2 * C + i];
+        csum[i] = t;
+    }
+    __syncthreads();
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += csum[c]; sq += csum[C + c]; }
+        part[2 * g] = su;
+        part[2 * g + 1] = sq;
+    }
+    cluster_sync_all();  // every CTA's partials are visible cluster-wide (release / acquire)
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int r = 0; r < cs; ++r) {  // fixed order: every CTA of the cluster gets bit-identical statistics
+            su += ld_dsmem_f32(part + 2 * g, r);
+            sq += ld_dsmem_f32(part + 2 * g + 1, r);
+        }
+        const float inv_n = 1.0f / (static_cast<float>(cpg) * HW);
+        const float mean = su * inv_n;
+        const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+        mr[2 * g] = mean;
+        mr[2 * g + 1] = rsqrtf(var + eps);
+        if (rank == 0 && stats_out) {  // {sum, sumsq}: what the backward kernels expect from the forward
+            stats_out[(b * groups + g) * 2] = su;
+            stats_out[(b * groups + g) * 2 + 1] = sq;
+        }
+    }
+    cluster_sync_all();  // remote reads of this CTA's partials are done (it may exit); mr[] visible to the whole block
+    if (pl >= lanes) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = vec * 8 + e, g = c / cpg;
+        sc[e] = mr[2 * g + 1] * gamma[c];
+        sh[e] = beta[c] - mr[2 * g] * sc[e];
+    }
+    for (int p = pl; p < npix; p += lanes) {
+        const long long pix = static_cast<long long>(b) * HW + p0 + p;
+        uint4 w;
+        if (TILE) {
+            w = *reinterpret_cast<const uint4*>(tile + static_cast<size_t>(p) * C + vec * 8);
+        } else {  // second read of the input (L2-resident: this CTA just streamed it); same fp16 rounding of the sum as the tile
+            float v[8];
+            load8(s, pix, vec * 8, v);
+            __half2* hw = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hw[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        }
+        if (raw) *reinterpret_cast<uint4*>(raw + pix * C + vec * 8) = w;
+        const __half2* h = reinterpret_cast<const __half2*>(&w);
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            float t0 = f.x * sc[2 * e] + sh[2 * e], t1 = f.y * sc[2 * e + 1] + sh[2 * e + 1];
+            if (silu) { t0 = silu_f(t0); t1 = silu_f(t1); }
+            oh[e] = __floats2half2_rn(t0, t1);
+        }
+        *reinterpret_cast<uint4*>(y + pix * C + vec * 8) = o;
     }
 }
 
@@ -218,9 +478,80 @@ extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stre
     s.x2 = reinterpret_cast<const __half*>(a->x2); s.add2 = reinterpret_cast<const __half*>(a->add2); s.s2 = a->add2_scale;
     s.c2 = a->x2 ? a->c2 : 0; s.ld2 = a->ld2;
     const int HW = a->hw, B = a->batch;
-    if (!a->stats_prezeroed &&
-        cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess)
-        return CTRLORA_ERR_CUDA;
+    // ---- single-pass cluster kernel where one image's slice per CTA fits in shared memory (CTRLORA_GN_CLUSTER=0 disables)
+    {
+        static int cl_env = -1;
+        if (cl_env < 0) {
+            const char* e = getenv("CTRLORA_GN_CLUSTER");
+            cl_env = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
+        }
+        const int vecs = C / 8;
+        const int lanes_max = vecs <= 512 ? 512 / vecs : 0;
+        auto fixed_for = [&](int lanes) {  // scratch [lanes][2C] + csum [2C] + part/mr [4 groups] + the staging mbarrier
+            return static_cast<size_t>((lanes + 1) * 2 * C + 4 * a->groups) * sizeof(float) + 16;
+        };
+        const size_t budget = 216 * 1024;
+        int cs = 0, mode = 0;
+        static int cl_max = -1;  // largest cluster used: 16-CTA clusters measured slower than the two-pass pair (profiles/README.md)
+        if (cl_max < 0) {
+            const char* e = getenv("CTRLORA_GN_CLUSTER_MAX");
+            cl_max = e ? atoi(e) : 8;
+        }
+        for (int c = 1; c <= cl_max && c <= 16 && cl_env && lanes_max > 0; c *= 2) {
+            const int ppc = (HW + c - 1) / c;
+            if (c > HW) break;
+            const int lanes = lanes_max < ppc ? lanes_max : ppc;
+            if (static_cast<size_t>(ppc) * C * 2 + fixed_for(lanes) <= budget) { cs = c; break; }
+        }
+        if (cs == 0 && cl_env == 2 && lanes_max > 0 && HW >= 16) { cs = 16; mode = 2; }  // CTRLORA_GN_CLUSTER=2: statistics-only cluster
+        if (cs > 0) {
+            const int ppc = (HW + cs - 1) / cs;
+            int lanes = lanes_max;
+            if (lanes > ppc) lanes = ppc;
+            if (lanes < 1) lanes = 1;
+            const size_t fixed = fixed_for(lanes);
+            const int threads = vecs * lanes;  // exact: the scratch layout is indexed by blockDim.x / vecs
+            // contiguous slice -> TMA bulk staging (needs 16-byte aligned base, dense rows)
+            if (mode != 2 && !a->x2 && !a->add1 && a->ld1 == C && (reinterpret_cast<uintptr_t>(a->x1) & 15) == 0) mode = 1;
+            const size_t smem = (mode == 2 ? 0 : static_cast<size_t>(ppc) * C * 2) + fixed;
+            static bool attr = false;
+            static int ok16 = -1;  // can a 16-CTA cluster of this kernel be co-scheduled on this part at all?
+            if (!attr) {
+                if (cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                    cudaFuncSetAttribute(gn_cluster_kernel<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                    cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                    cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                    cudaFuncSetAttribute(gn_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                    cudaFuncSetAttribute(gn_cluster_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+                    return CTRLORA_ERR_CUDA;
+                attr = true;
+            }
+            if (cs == 16 && ok16 < 0) {
+                cudaLaunchConfig_t qc;
+                memset(&qc, 0, sizeof(qc));
+                qc.gridDim = dim3(16, 1);
+                qc.blockDim = dim3(512);
+                qc.dynamicSmemBytes = 216 * 1024;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                qc.attrs = qa;
+                qc.numAttrs = 1;
+                int nclusters = 0;
+                ok16 = (cudaOccupancyMaxActiveClusters(&nclusters, gn_cluster_kernel<0>, &qc) == cudaSuccess && nclusters >= 1) ? 1 : 0;
+                (void)cudaGetLastError();
+            }
+            if (cs == 16 && ok16 == 0) goto two_pass;
+            const cudaError_t rc = launch_cluster_pdl(mode == 1 ? gn_cluster_kernel<1> : mode == 2 ? gn_cluster_kernel<2> : gn_cluster_kernel<0>,
+                                                      dim3(cs, B),
+                                                      dim3(threads), smem, stream, (unsigned)cs, s, C, HW, (int)a->groups, ppc, cs,
+                                                      a->gamma, a->beta, a->eps, (int)a->silu, reinterpret_cast<__half*>(a->y),
+                                                      reinterpret_cast<__half*>(a->raw_out), reinterpret_cast<float*>(a->stats_ws));
+            if (rc == cudaSuccess) return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+            (void)cudaGetLastError();  // fall through to the two-pass pair
+        }
+    }
+two_pass:
     // ~4 blocks per SM in total, at least 8 pixels per block
     int chunks = (592 + B - 1) / B;
     int ppb = (HW + chunks - 1) / chunks;
@@ -230,8 +561,16 @@ extern "C" int ctrlora_groupnorm_f16(const ctrlora_groupnorm_args* a, void* stre
     const int vecs = C / 8;
     const int lanes = vecs >= 256 ? 1 : 256 / vecs;
     const int threads = vecs * lanes;  // every thread owns one 8-channel vector of one pixel lane
+    const bool det = a->partial_ws && a->partial_counters && B <= a->partial_counters_len &&
+                     static_cast<long long>(B) * chunks * a->groups * 2 <= a->partial_ws_floats;
+    if (!det && !a->stats_prezeroed &&
+        cudaMemsetAsync(a->stats_ws, 0, sizeof(float) * 2 * B * a->groups, stream) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
     // after a memset node the stats kernel is a plain launch; with a pre-zeroed workspace it chains programmatically
-    if (a->stats_prezeroed)
+    if (det)
+        launch_pdl(gn_stats_det_kernel, grid, dim3(threads), (size_t)((lanes + 1) * 2 * C * sizeof(float)), stream, s, C, HW,
+                   (int)a->groups, ppb, reinterpret_cast<float*>(a->stats_ws), a->partial_ws, a->partial_counters);
+    else if (a->stats_prezeroed)
         launch_pdl(gn_stats_kernel, grid, dim3(threads), (size_t)(2 * C * sizeof(float)), stream, s, C, HW, (int)a->groups, ppb,
                    reinterpret_cast<float*>(a->stats_ws));
     else

@@ -208,11 +208,12 @@ class ControlLDM(LatentDiffusion):
     def apply_model(self, x_noisy, t, cond, *args, **kwargs):
         assert isinstance(cond, dict)
         diffusion_model = self.model.diffusion_model
-        cond_txt = torch.cat(cond['c_crossattn'], 1)
+        cond_txt = cond['c_crossattn'][0] if len(cond['c_crossattn']) == 1 else torch.cat(cond['c_crossattn'], 1)
         if cond['c_concat'] is None:
             return diffusion_model(x=x_noisy, timesteps=t, context=cond_txt, control=None,
                                    only_mid_control=self.only_mid_control)
-        control = self.control_model(x=x_noisy, hint=torch.cat(cond['c_concat'], 1), timesteps=t, context=cond_txt)
+        hint = cond['c_concat'][0] if len(cond['c_concat']) == 1 else torch.cat(cond['c_concat'], 1)
+        control = self.control_model(x=x_noisy, hint=hint, timesteps=t, context=cond_txt)
         return diffusion_model(x=x_noisy, timesteps=t, context=cond_txt, control=self.scaled_control(control),
                                only_mid_control=self.only_mid_control)
 

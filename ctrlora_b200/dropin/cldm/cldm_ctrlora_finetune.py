@@ -64,7 +64,7 @@ class ControlFinetuneLDM(ControlLDM):
     def apply_model(self, x_noisy, t, cond, *args, **kwargs):
         assert isinstance(cond, dict)
         diffusion_model = self.model.diffusion_model
-        cond_txt = torch.cat(cond['c_crossattn'], 1)
+        cond_txt = cond['c_crossattn'][0] if len(cond['c_crossattn']) == 1 else torch.cat(cond['c_crossattn'], 1)
         if cond['c_concat'] is None:
             return diffusion_model(x=x_noisy, timesteps=t, context=cond_txt, control=None,
                                    only_mid_control=self.only_mid_control)

@@ -89,7 +89,8 @@ class ControlInferenceLDM(ControlLDM):
         assert len(conds) == self.control_model.lora_num
         assert len(self.lora_weights) == self.control_model.lora_num
         diffusion_model = self.model.diffusion_model
-        cond_txt = torch.cat(conds[0]['c_crossattn'], 1)
+        cc = conds[0]['c_crossattn']
+        cond_txt = cc[0] if len(cc) == 1 else torch.cat(cc, 1)
         stacks = []
         for i, cond in enumerate(conds):
             self.control_model.switch_lora(i)

@@ -102,14 +102,15 @@ class DDIMSampler(object):
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
             timesteps = self.ddim_timesteps[:subset_end]
         intermediates = {'x_inter': [img], 'pred_x0': [img]}
-        time_range = reversed(range(0, timesteps)) if ddim_use_original_steps else np.flip(timesteps)
+        time_range = list(reversed(range(0, timesteps))) if ddim_use_original_steps else np.flip(timesteps)
         total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
         if verbose:
             print(f"Running DDIM Sampling with {total_steps} timesteps")
         iterator = tqdm(time_range, desc='DDIM Sampler', total=total_steps, disable=not verbose)
+        ts_all = self._step_tensors(time_range, b, device)  # every step's `ts` in one host->device copy
         for i, step in enumerate(iterator):
             index = total_steps - i - 1
-            ts = torch.full((b,), int(step), device=device, dtype=torch.long)
+            ts = ts_all[i]
             if mask is not None:
                 assert x0 is not None
                 img_orig = self.model.q_sample(x0, ts)
@@ -132,6 +133,13 @@ class DDIMSampler(object):
                 intermediates['x_inter'].append(img)
                 intermediates['pred_x0'].append(pred_x0)
         return img, intermediates
+
+    @staticmethod
+    def _step_tensors(steps, batch, device):
+        """int64 [len(steps), batch]: row i is the reference's `torch.full((b,), step)` of step i (ddim_hacked.py:152)"""
+        steps = [int(v) for v in steps]
+        host = torch.tensor(steps, dtype=torch.long)[:, None].expand(len(steps), batch).contiguous()
+        return host.to(device, non_blocking=False)
 
     # ---------------------------------------------------------------------------------------------- eps prediction
     @staticmethod
@@ -281,10 +289,9 @@ class DDIMSampler(object):
         """Run the last `t_start` sampler steps from x_latent (reference :298-317)."""
         steps = (np.arange(self.ddpm_num_timesteps) if use_original_steps else self.ddim_timesteps)[:t_start]
         x_dec = x_latent
-        ts = torch.empty((x_latent.shape[0],), device=x_latent.device, dtype=torch.long)
+        ts_all = self._step_tensors(steps, x_latent.shape[0], x_latent.device)
         for i, index in enumerate(range(len(steps) - 1, -1, -1)):
-            ts.fill_(int(steps[index]))
-            x_dec, _ = self.p_sample_ddim(x_dec, cond, ts, index=index, use_original_steps=use_original_steps,
+            x_dec, _ = self.p_sample_ddim(x_dec, cond, ts_all[index], index=index, use_original_steps=use_original_steps,
                                           unconditional_guidance_scale=unconditional_guidance_scale,
                                           unconditional_conditioning=unconditional_conditioning)
             if callback:
@@ -309,11 +316,10 @@ class DDIMSampler(object):
             # 0-dim float64 tensor multiplies an fp32 tensor
         use_cfg = not (unconditional_guidance_scale == 1. or unconditional_conditioning is None)
         x_next, kept, kept_steps = x0, [], []
-        t = torch.empty((x0.shape[0],), device=x0.device, dtype=torch.long)
+        ts_all = self._step_tensors(steps[:t_enc], x0.shape[0], x0.device)
         every = (t_enc // return_intermediates) if return_intermediates else 0
         for i in range(t_enc):
-            t.fill_(int(steps[i]))
-            e_c, e_u = self._eps_pair(x_next, t, c, unconditional_conditioning, use_cfg)
+            e_c, e_u = self._eps_pair(x_next, ts_all[i], c, unconditional_conditioning, use_cfg)
             an, a = a_next_tab[i], a_tab[i]
             c1 = (an / a).sqrt()
             c2 = an.sqrt() * ((1 / an - 1).sqrt() - (1 / a - 1).sqrt())

@@ -120,7 +120,9 @@ class CrossAttention(nn.Module):
                                 lambda: prepare.effective_linear_weight(self.to_q))
             q = ops.gemm(x2d, wq)
             k = torch.empty((batch * nk, inner), device=dev, dtype=torch.float16)
-            vt = torch.empty((batch, h, d, nk_pad), device=dev, dtype=torch.float16)
+            # key padding columns (77 -> 80) are never written by the projection: they must hold finite values (their
+            # probabilities are exactly 0, but 0 x NaN from recycled memory would poison the row) -> zero-initialised
+            vt = (torch.zeros if nk_pad != nk else torch.empty)((batch, h, d, nk_pad), device=dev, dtype=torch.float16)
             w = self._cat_weight("kv", [self.to_k, self.to_v])
             ops.gemm(ctx2d, w, seg_outs=[k, vt], seg_width=inner, transposed=(0, 1, 0), rows_per_img=nk, head_dim=d,
                      tok_pad=nk_pad)

@@ -283,6 +283,19 @@ def _stats_take(device, n):
     return torch.empty(n, device=device, dtype=torch.float32), 0
 
 
+_GN_PARTIAL = {}  # device index -> (fp32 scratch for per-block partial statistics, uint32 self-cleaning arrival counters)
+GN_PARTIAL_FLOATS = 1 << 19
+GN_PARTIAL_COUNTERS = 256
+
+
+def _gn_partial_buffers(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _GN_PARTIAL:
+        _GN_PARTIAL[key] = (torch.empty(GN_PARTIAL_FLOATS, device=device, dtype=torch.float32),
+                            torch.zeros(GN_PARTIAL_COUNTERS, device=device, dtype=torch.int32))
+    return _GN_PARTIAL[key]
+
+
 def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None, add2_scale=1.0,
               groups=32, want_raw=False, stats_ws=None, want_stats=False):
     """GroupNorm(+SiLU) over [x1 (+s1*add1) | x2 (+s2*add2)], pixel-major fp16 [B,H,W,C*]; returns y (and raw concat)."""
@@ -309,6 +322,10 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == ctot
     a.gamma, a.beta, a.eps, a.silu = _dp(gamma), _dp(beta), float(eps), int(silu)
     a.y, a.raw_out, a.stats_ws = _dp(y), _dp(raw), _dp(stats_ws)
+    if not torch.cuda.is_current_stream_capturing() or x1.device.index in _GN_PARTIAL or torch.cuda.current_device() in _GN_PARTIAL:
+        pws, pcnt = _gn_partial_buffers(x1.device)  # (never first allocated inside a capture)
+        a.partial_ws, a.partial_ws_floats = _dp(pws), GN_PARTIAL_FLOATS
+        a.partial_counters, a.partial_counters_len = _dp(pcnt), GN_PARTIAL_COUNTERS
     _count(2)
     check(_lib.load().ctrlora_groupnorm_f16(C.addressof(a), _sp()), "ctrlora_groupnorm_f16")
     if want_stats:

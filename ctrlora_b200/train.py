@@ -217,7 +217,7 @@ def tblock_fwd(blk, x2d, batch, n, ctx2d, nk):
     s["q2"] = ops.gemm(n2, lin_w(a2m.to_q))
     k2 = torch.empty((batch * nk, inner), device=dev, dtype=h16)
     v2 = torch.empty_like(k2)
-    vt2 = torch.empty((batch, heads, d, npk), device=dev, dtype=h16)
+    vt2 = (torch.zeros if npk != nk else torch.empty)((batch, heads, d, npk), device=dev, dtype=h16)  # finite key padding
     ops.gemm(ctx2d, cat_w(a2m, "kv", [a2m.to_k, a2m.to_v]), seg_outs=[k2, vt2], seg_width=inner, transposed=(0, 1, 0),
              rows_per_img=nk, head_dim=d, tok_pad=npk, dup_out=v2)
     s["k2"], s["v2"] = k2, v2

@@ -167,5 +167,7 @@ def test_graph_follows_load_state_dict(g):
     eager = DDIMSampler(model, use_cuda_graph=False)
     eager.make_schedule(50, ddim_eta=0.0, verbose=False)
     x3, _ = eager.p_sample_ddim(d["x"], cond, ts, **kw)
-    assert rel(x2, x3) < 1e-6, "graph replayed stale weights"
-    assert rel(x2, x1) > 1e-3
+    # stale folded weights would leave x2 near x1 (the two checkpoints differ by ~0.2); run-to-run noise of the tiny network
+    # is ~1e-3 (tools/debug_determinism.py)
+    assert rel(x2, x3) < 5e-3, "graph replayed stale weights"
+    assert rel(x2, x1) > 5e-2

@@ -21,7 +21,7 @@ TOL = {
     "tiny_control": 2.5e-3,      # 13 residuals x 5 attached LoRA sets: worst 2.08e-3
     "tiny_sample": 4.7e-3,       # 4-step sampling 3.9e-3, pred_x0 4.6e-3 (divides the eps error by sqrt(alpha_t) ~ 0.07 at t = 981)
     "tiny_loss": 2e-4,           # 6.6e-5
-    "tiny_grad_norm": 3.5e-3,    # worst of 246 tensors: 2.4e-3 (2.8e-3 with only_mid_control)
+    "tiny_grad_norm": 4.6e-3,    # worst of 246 (finetune) / 816 (pretrain) tensors over runs: 2.4e-3 .. 3.8e-3
     "tiny_grad_tensor": 7e-3,    # worst of 16 full tensors: 5.5e-3
     "mid_eps": 1.7e-3,           # 1.41e-3
     "sd15_eps": 1.9e-3,          # SD1.5 + ControlNet rank 128: 1.55e-3 (forward), 1.57e-3 (training forward, B = 2)
@@ -29,8 +29,8 @@ TOL = {
     "sd15_loss": 1e-4,           # 2.3e-5
     "sd15_grad_norm": 1.2e-3,    # worst of the 246 gradient norms 9.4e-4 (median 3.7e-4)
     "sd15_grad_tensor": 2.3e-3,  # worst of 10 full tensors 1.9e-3
-    "vae_encode": 3e-3,          # first-stage VAE (bounds to be tightened to measured + 20 % once measured)
-    "vae_decode": 3e-3,
+    "vae_encode": 2e-3,          # first-stage VAE: tiny moments 1.22e-3, SD VAE at 512x512 moments 1.62e-3
+    "vae_decode": 3.5e-3,        # tiny decode 1.37e-3, encode->decode round trip 2.91e-3; SD VAE decode 1.56e-3
 }
 
 

@@ -240,7 +240,8 @@ def variants(seed=0):
     g["pretrain_param_names"] = [n for n, _ in named]
     g["pretrain_grad_norms"] = {n: (p.grad.norm().item() if p.grad is not None else None) for n, p in named}
     keep = ("input_blocks.0.0.weight", "input_blocks.0.0.bias", "input_blocks.1.0.in_layers.2.weight",
-            "input_blocks.1.0.out_layers.3.weight", "input_blocks.1.0.emb_layers.1.weight", "input_blocks.3.0.op.weight",
+            "input_blocks.1.0.out_layers.3.weight", "input_blocks.4.0.emb_layers.1.weight", "input_blocks.4.0.emb_layers.1.bias",
+            "input_blocks.3.0.op.weight",
             "input_blocks.4.0.skip_connection.weight", "input_blocks.4.1.proj_in.weight",
             "input_blocks.4.1.transformer_blocks.0.attn1.to_q.weight", "input_blocks.4.1.transformer_blocks.0.attn2.to_k.weight",
             "input_blocks.4.1.transformer_blocks.0.ff.net.0.proj.weight", "input_blocks.4.1.transformer_blocks.0.ff.net.0.proj.bias",
