@@ -92,7 +92,8 @@ _ARGTYPES = {
     "ctrlora_upsample2x_bwd_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_im2col_s2_bwd_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_mse_loss_grad": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
-    "ctrlora_adamw_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P],
+    "ctrlora_adamw_f32": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P, _P],
+    "ctrlora_adamw_begin": [_P, _P, _F, _F, _P, _P, _P],
     "ctrlora_nonfinite_flag_f32": [_P, _L, _P, _P],
     "ctrlora_im2col_3x3_f16": [_P, _P, _I, _I, _I, _I, _P],
     "ctrlora_outer_accum_f32": [_P, _I, _P, _I, _P, _L, _I, _I, _I, _F, _F, _I, _P],
@@ -102,6 +103,7 @@ _ARGTYPES = {
     "ctrlora_im2col_s2_pad_f16": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ctrlora_softmax_rows_f32_to_f16": [_P, _L, _P, _L, _L, _I, _F, _P],
     "ctrlora_gaussian_sample": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "ctrlora_memset_zero": [_P, _L, _P],
     "ctrlora_q_sample": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "ctrlora_ddim_encode_update": [_P, _P, _P, _P, _I, _F, _F, _F, _P],
     "ctrlora_weighted_sum_f16": [_P, _P, _I, _P, _L, _P],
@@ -154,9 +156,11 @@ EXPORTS = [
     "ctrlora_im2col_s2_bwd_f16",
     "ctrlora_mse_loss_grad",
     "ctrlora_adamw_f32",
+    "ctrlora_adamw_begin",
     "ctrlora_nonfinite_flag_f32",
     "ctrlora_weighted_sum_f16",
     "ctrlora_q_sample",
+    "ctrlora_memset_zero",
     "ctrlora_im2col_s2_pad_f16",
     "ctrlora_softmax_rows_f32_to_f16",
     "ctrlora_gaussian_sample",

@@ -787,6 +787,12 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
             const int buf_bytes = nfull * 16384 + tail * 8192;
             int nbuf = 2;
             if ((GEMM_SMEM_DATA - 2 * buf_bytes) / p.stage_bytes < 3) nbuf = 1;
+            static int nbuf_env = -1;  // CTRLORA_GEMM_EPI_NBUF=1: single staging buffer -> one or two more ring stages in flight
+            if (nbuf_env < 0) {
+                const char* e = getenv("CTRLORA_GEMM_EPI_NBUF");
+                nbuf_env = e ? atoi(e) : 0;
+            }
+            if (nbuf_env == 1) nbuf = 1;
             if ((GEMM_SMEM_DATA - nbuf * buf_bytes) / p.stage_bytes >= 3) {
                 p.epi_tma = 1; p.epi_nbuf = nbuf; p.epi_res = a->residual ? 1 : 0;
                 p.epi_nfull = nfull; p.epi_tail = tail; p.epi_buf_bytes = buf_bytes;

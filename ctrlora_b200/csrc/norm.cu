@@ -345,19 +345,25 @@ gn_cluster_kernel(GnSrc s, int C, int HW, int groups, int ppc, int cs, const flo
     }
     __syncthreads();
     const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float su = 0.f, sq = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += csum[c]; sq += csum[C + c]; }
-        part[2 * g] = su;
-        part[2 * g + 1] = sq;
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {  // one thread per (group, statistic), fixed channel order
+        const int g = i >> 1, which = i & 1;
+        float t = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) t += csum[which * C + c];
+        part[i] = t;
     }
     cluster_sync_all();  // every CTA's partials are visible cluster-wide (release / acquire)
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float su = 0.f, sq = 0.f;
-        for (int r = 0; r < cs; ++r) {  // fixed order: every CTA of the cluster gets bit-identical statistics
-            su += ld_dsmem_f32(part + 2 * g, r);
-            sq += ld_dsmem_f32(part + 2 * g + 1, r);
+        // all remote loads are issued before the first add (a dependent load -> add chain would serialise ~0.7 us of
+        // DSMEM latency per CTA of the cluster); the adds run in rank order: every CTA gets bit-identical statistics
+        float rs[16], rq[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            rs[r] = r < cs ? ld_dsmem_f32(part + 2 * g, r) : 0.f;
+            rq[r] = r < cs ? ld_dsmem_f32(part + 2 * g + 1, r) : 0.f;
         }
+        float su = 0.f, sq = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { su += rs[r]; sq += rq[r]; }
         const float inv_n = 1.0f / (static_cast<float>(cpg) * HW);
         const float mean = su * inv_n;
         const float var = fmaxf(sq * inv_n - mean * mean, 0.f);

@@ -173,10 +173,11 @@ __global__ void mse_loss_grad_kernel(const float* __restrict__ eps, const float*
 // torch.optim.AdamW semantics (decoupled weight decay, bias correction), fp32 master params, one flat buffer.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-                             float grad_scale, const int* __restrict__ skip_flag) {
+                             float grad_scale, const int* __restrict__ skip_flag, const float* __restrict__ bc_dev) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (skip_flag && *skip_flag) return;  // a non-finite gradient was seen this step (loss-scale overflow): no update
+    if (bc_dev) { bc1 = bc_dev[0]; bc2 = bc_dev[1]; }  // bias corrections of the DEVICE-side step counter (adamw_begin)
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
@@ -299,6 +300,22 @@ __global__ void cast_rows_kernel(const float* __restrict__ src, long long lds, _
     dst[i] = __float2half_rn(src[(i / cols) * lds + (i % cols)]);
 }
 
+// One thread, in front of an AdamW step: advances the device-side step counter unless the step is being skipped (then the
+// skipped-steps counter), and leaves the two bias corrections 1 - beta^step in bc[0..1].  With the counter on the device the
+// host never has to read the overflow flag before launching the next step (it polls `skipped` now and then to lower the loss
+// scale), and torch's `step` semantics -- a skipped step does not count -- hold exactly.
+__global__ void adamw_begin_kernel(int* __restrict__ step_counter, const int* __restrict__ skip_flag, float beta1, float beta2,
+                                   float* __restrict__ bc, int* __restrict__ skipped) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (skip_flag && *skip_flag) {
+        if (skipped) ++*skipped;
+        return;
+    }
+    const int st = ++*step_counter;
+    bc[0] = 1.0f - powf(beta1, static_cast<float>(st));
+    bc[1] = 1.0f - powf(beta2, static_cast<float>(st));
+}
+
 static inline unsigned nblk(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace ctrl
@@ -376,11 +393,18 @@ extern "C" int ctrlora_mse_loss_grad(const float* eps, const float* noise, float
 
 extern "C" int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                                 const int* skip_flag, void* stream) {
-    if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) return CTRLORA_ERR_ARG;
+                                 const int* skip_flag, const float* bc_dev, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || (step < 1 && !bc_dev)) return CTRLORA_ERR_ARG;
     const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     adamw_kernel<<<nblk(n, 256), 256, 0, STREAM(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                           weight_decay, bc1, bc2, grad_scale, skip_flag);
+                                                           weight_decay, bc1, bc2, grad_scale, skip_flag, bc_dev);
+    return LAUNCH_OK();
+}
+
+extern "C" int ctrlora_adamw_begin(int* step_counter, const int* skip_flag, float beta1, float beta2, float* bc, int* skipped,
+                                   void* stream) {
+    if (!step_counter || !bc) return CTRLORA_ERR_ARG;
+    adamw_begin_kernel<<<1, 32, 0, STREAM(stream)>>>(step_counter, skip_flag, beta1, beta2, bc, skipped);
     return LAUNCH_OK();
 }
 

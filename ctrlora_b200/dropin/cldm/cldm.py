@@ -21,7 +21,8 @@ from ldm.util import exists, instantiate_from_config  # noqa: F401
 
 
 def _ctx16(context):
-    return None if context is None else to_f16_rows(context).view(context.shape[0], context.shape[1], -1)
+    from ctrlora_b200.runtime import context_f16
+    return context_f16(context)
 
 
 class ControlledUnetModel(UNetModel):
@@ -200,6 +201,32 @@ class ControlLDM(LatentDiffusion):
             self.__dict__["_hint_cache"] = (key, lat)
             return lat
         return self.get_first_stage_encoding(self.encode_first_stage(hint))
+
+    @torch.no_grad()
+    def prepare_context(self, context):
+        """Register `context` ([B, 77, 768], the tensor apply_model will receive as c_crossattn[0]) as step-invariant:
+        its fp16 copy and the K / V^T projections of every cross-attention layer of the ControlNet and the UNet are
+        computed now, into persistent buffers, and re-used by every following apply_model on this same tensor (identity +
+        version checked; weight changes re-project).  Idempotent and cheap when nothing changed."""
+        from ctrlora_b200 import runtime
+        from ldm.modules.attention import CrossAttention
+        if context is None or not context.is_cuda:
+            return
+        reg = runtime.CTX16
+        if not runtime.context_registered(context):
+            ctx16 = runtime.to_f16_rows(context).view(context.shape[0], context.shape[1], -1)
+            old = reg["ctx16"]
+            if old is not None and old.shape == ctx16.shape and old.device == ctx16.device:
+                old.copy_(ctx16)  # keep the address: captured graphs read this buffer
+                ctx16 = old
+            reg.update(tensor=context, version=context._version, ctx16=ctx16, epoch=reg["epoch"] + 1)
+        ctx16 = reg["ctx16"]
+        key = reg["epoch"]
+        ctx2d, nk = ctx16.view(-1, ctx16.shape[-1]), ctx16.shape[1]
+        for net in (self.control_model, self.model.diffusion_model):
+            for m in net.modules():
+                if isinstance(m, CrossAttention) and m.to_k.in_features == ctx16.shape[-1] and m.to_k.in_features != m.to_q.in_features:
+                    m.project_context(ctx2d, ctx16.shape[0], nk, key)
 
     def scaled_control(self, control):
         return [Scaled(c, s) for c, s in zip(control, self.control_scales)]

@@ -86,6 +86,7 @@ class _LoRAFuseMixin:
         fused, w_up = _fused(self.weight.data, lora.up.weight.data, lora.down.weight.data, lora.network_alpha, lora.rank,
                              lora_scale, safe_fusing, self)
         self.weight.data = fused.to(device=device, dtype=dtype)
+        prepare.bump_struct_version()
         self.lora_layer = None
         self.w_up = w_up.cpu()
         self.w_down = lora.down.weight.data.float().cpu()
@@ -99,6 +100,7 @@ class _LoRAFuseMixin:
         w_up, w_down = self.w_up.to(device).float(), self.w_down.to(device).float()
         fusion = torch.mm(w_up.flatten(start_dim=1), w_down.flatten(start_dim=1)).reshape(fused.shape)
         self.weight.data = (fused.float() - self._lora_scale * fusion).to(device=device, dtype=dtype)
+        prepare.bump_struct_version()
         self.w_up = None
         self.w_down = None
 

@@ -349,7 +349,8 @@ class UNetModel(nn.Module):
         assert y is None, "class-conditional UNets are not on the CtrLoRA path"
         hs = []
         emb = self.embed(timesteps)
-        ctx = None if context is None else to_f16_rows(context).view(context.shape[0], context.shape[1], -1)
+        from ctrlora_b200.runtime import context_f16
+        ctx = context_f16(context)
         h = x
         for module in self.input_blocks:
             h = module(h, emb, ctx)

@@ -333,6 +333,13 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
     return (y, raw) if want_raw else y
 
 
+def zeros(shape, device, dtype=torch.float16):
+    """torch.empty + cudaMemsetAsync (a memset node; torch.zeros launches an ATen fill kernel)"""
+    t = torch.empty(shape, device=device, dtype=dtype)
+    check(_lib.load().ctrlora_memset_zero(_dp(t), t.numel() * t.element_size(), _sp()), "memset_zero")
+    return t
+
+
 def layernorm(x, gamma, beta, eps=1e-5):
     """x fp16 [..., C] with contiguous last dim and uniform row stride."""
     _require_cuda(x)
@@ -693,14 +700,23 @@ def mse_loss_grad(eps, noise, c_pad=8, grad_scale=1.0):
 
 
 def adamw_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-               grad_scale=1.0, skip_flag=None):
+               grad_scale=1.0, skip_flag=None, bc_dev=None):
     """In-place AdamW over flat fp32 buffers (torch.optim.AdamW semantics).  skip_flag: device int32 [1]; non-zero =
-    the step is skipped (non-finite gradients under loss scaling)."""
+    the step is skipped (non-finite gradients under loss scaling).  bc_dev: device fp32 [2] bias corrections from
+    adamw_begin (then `step` is ignored)."""
     _require_cuda(params, grads)
     _count()
     check(_lib.load().ctrlora_adamw_f32(_dp(params), _dp(grads), _dp(exp_avg), _dp(exp_avg_sq), params.numel(), float(lr),
                                         float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
-                                        float(grad_scale), _dp(skip_flag), _sp()), "adamw")
+                                        float(grad_scale), _dp(skip_flag), _dp(bc_dev), _sp()), "adamw")
+
+
+def adamw_begin(step_counter, skip_flag, betas, bc, skipped=None):
+    """device-side step bookkeeping in front of adamw_step (see ctrlora_adamw_begin)"""
+    _require_cuda(step_counter, bc)
+    _count()
+    check(_lib.load().ctrlora_adamw_begin(_dp(step_counter), _dp(skip_flag), float(betas[0]), float(betas[1]), _dp(bc),
+                                          _dp(skipped), _sp()), "adamw_begin")
 
 
 def nonfinite_flag(x, flag):

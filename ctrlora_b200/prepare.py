@@ -19,6 +19,17 @@ def bump_train_version():
     TRAIN_VERSION += 1
 
 
+# Bumped whenever this package re-points a parameter's storage (`p.data = ...`: LoRA fuse / unfuse, a trainer adopting the
+# parameters into its flat buffer) -- a change torch's `_version` counter does not see.  Captured-graph owners (the sampler)
+# compare it every call and re-verify the storage pointers themselves only at the start of a sampling run.
+STRUCT_VERSION = 0
+
+
+def bump_struct_version():
+    global STRUCT_VERSION
+    STRUCT_VERSION += 1
+
+
 def _ver(*params):
     return tuple((p.data_ptr(), p._version, tuple(p.shape), TRAIN_VERSION if getattr(p, "_ctrlora_trainable", False) else 0)
                  if p is not None else None for p in params)

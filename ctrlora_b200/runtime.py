@@ -29,6 +29,27 @@ def nchw_view(buf):
     return buf.permute(0, 3, 1, 2)
 
 
+# Step-invariant text conditioning (one sampling run = 50 DDIM steps over the SAME [B,77,768] context): the fp16 copy of the
+# context and every cross-attention's K / V^T projections of it are computed once by `prepare_context` (called by the sampler)
+# and found again here by tensor identity, instead of 32 small GEMMs + a cast per step (1.8 % of the DDIM step).
+CTX16 = {"tensor": None, "version": -1, "ctx16": None, "epoch": 0}
+# The registered tensor is held by reference (so its address cannot be recycled for another tensor while the cache lives) and
+# matched by object identity + torch's in-place version counter.
+
+
+def context_registered(context):
+    return CTX16["tensor"] is context and CTX16["version"] == context._version
+
+
+def context_f16(context):
+    """[B, T, D] context -> fp16 [B, T, D]; the cached copy when `prepare_context` registered this very tensor."""
+    if context is None:
+        return None
+    if context_registered(context):
+        return CTX16["ctx16"]
+    return to_f16_rows(context).view(context.shape[0], context.shape[1], -1)
+
+
 def to_f16_rows(t):
     """fp32/fp16 [..., K] -> fp16 [rows, K] contiguous (context tokens)."""
     k = t.shape[-1]

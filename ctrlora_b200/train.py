@@ -70,6 +70,7 @@ class GradSink:
             self.offsets[name] = (off, n)
             off += n
         self.numel = total
+        prepare.bump_struct_version()  # parameter storages were re-pointed into the flat buffer
 
     def grad(self, param):
         """fp32 gradient view of a trainable parameter in STORAGE order (conv weights: [Cout, taps*Cin]), or None if the
@@ -132,13 +133,28 @@ def lora_grads(lin, x2d, dy2d, G):
     scale = 1.0 if lora.network_alpha is None else lora.network_alpha / lora.rank
     r, k = lora.down.weight.shape
     n = lora.up.weight.shape[0]
+    rp = (r + 7) // 8 * 8  # the token-major operands need 16-byte rows: ranks that are not a multiple of 8 are zero-padded
     c = _cache(lora)
-    d16 = c.get("d16", [lora.down.weight], lambda: prepare.linear_weight(lora.down.weight))           # [r, 1, K]
-    u16t = c.get("u16t", [lora.up.weight], lambda: ops.cast_transpose(f32(lora.up.weight), 1, n, r).view(r, 1, n))  # [r, 1, N]
-    t1 = ops.gemm(x2d, d16)        # X Down^T   [M, r]
-    ops.wgrad_tn(dy2d, t1, out=g_up, alpha=scale, beta=1.0)
-    t2 = ops.gemm(dy2d, u16t)      # dY Up      [M, r]
-    ops.wgrad_tn(t2, x2d, out=g_down, alpha=scale, beta=1.0)
+
+    def padded(w16, rows):  # fp16 [r, 1, cols] -> [rp, 1, cols] with zero rows
+        if rp == r:
+            return w16
+        out = ops.zeros((rp, 1, rows), w16.device)
+        out[:r].copy_(w16)
+        return out
+
+    d16 = c.get("d16", [lora.down.weight], lambda: padded(prepare.linear_weight(lora.down.weight), k))                       # [rp, 1, K]
+    u16t = c.get("u16t", [lora.up.weight], lambda: padded(ops.cast_transpose(f32(lora.up.weight), 1, n, r).view(r, 1, n), n))  # [rp, 1, N]
+    t1 = ops.gemm(x2d, d16)        # X Down^T   [M, rp]
+    t2 = ops.gemm(dy2d, u16t)      # dY Up      [M, rp]
+    if rp == r:
+        ops.wgrad_tn(dy2d, t1, out=g_up, alpha=scale, beta=1.0)
+        ops.wgrad_tn(t2, x2d, out=g_down, alpha=scale, beta=1.0)
+    else:
+        tmp_up = ops.wgrad_tn(dy2d, t1, alpha=scale)             # [N, rp]: columns r.. are zero
+        ops.copy2d(tmp_up, g_up, n, r, rp, r, accumulate=True)
+        tmp_down = ops.wgrad_tn(t2, x2d, alpha=scale)            # [rp, K]: rows r.. are zero
+        ops.copy2d(tmp_down, g_down, r, k, k, k, accumulate=True)
 
 
 def dense_lin_grads(lin, x2d, dy2d, G):
@@ -217,7 +233,7 @@ def tblock_fwd(blk, x2d, batch, n, ctx2d, nk):
     s["q2"] = ops.gemm(n2, lin_w(a2m.to_q))
     k2 = torch.empty((batch * nk, inner), device=dev, dtype=h16)
     v2 = torch.empty_like(k2)
-    vt2 = (torch.zeros if npk != nk else torch.empty)((batch, heads, d, npk), device=dev, dtype=h16)  # finite key padding
+    vt2 = ops.zeros((batch, heads, d, npk), dev) if npk != nk else torch.empty((batch, heads, d, npk), device=dev, dtype=h16)  # finite key padding
     ops.gemm(ctx2d, cat_w(a2m, "kv", [a2m.to_k, a2m.to_v]), seg_outs=[k2, vt2], seg_width=inner, transposed=(0, 1, 0),
              rows_per_img=nk, head_dim=d, tok_pad=npk, dup_out=v2)
     s["k2"], s["v2"] = k2, v2
@@ -668,11 +684,42 @@ class FinetuneTrainer:
         # it out of the fp32 gradient buffer.  `dynamic`: a non-finite gradient skips the update and halves the scale.
         self.loss_scale = loss_scale
         self.dynamic_loss_scale = dynamic_loss_scale
-        self.overflow_flag = torch.zeros(1, device=self.G.flat_p.device, dtype=torch.int32)
+        dev = self.G.flat_p.device
+        self.overflow_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         self.skipped_steps = 0
+        self._init_step_state(dev)
 
     LOSS_SCALE_DIV = 8.0
-    CHECK_OVERFLOW_EVERY = 1
+    CHECK_OVERFLOW_EVERY = 16   # host polls the device-side skipped-steps counter this often (no per-step sync)
+
+    def _init_step_state(self, dev):
+        """AdamW's step counter lives on the device (ops.adamw_begin): a step skipped for a non-finite gradient does not
+        count, and the host does not have to read the overflow flag before it may launch the next step."""
+        self._step_dev = {}            # segment key -> int32 [1] step counter
+        self._bc_dev = {}              # segment key -> fp32 [2] bias corrections of the current step
+        self._skipped_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._skipped_seen = 0
+        self._launched = 0
+
+    def _seg_state(self, key):
+        if key not in self._step_dev:
+            dev = self.G.flat_p.device
+            self._step_dev[key] = torch.zeros(1, device=dev, dtype=torch.int32)
+            self._bc_dev[key] = torch.ones(2, device=dev, dtype=torch.float32)
+        return self._step_dev[key], self._bc_dev[key]
+
+    def _poll_overflow(self, force=False):
+        """True (after halving the loss scale and re-capturing) if the device skipped steps since the last poll."""
+        self._launched += 1
+        if not (force or (self.dynamic_loss_scale and self._launched % self.CHECK_OVERFLOW_EVERY == 0)):
+            return False
+        skipped = int(self._skipped_dev.item())
+        if skipped == self._skipped_seen:
+            return False
+        self.skipped_steps += skipped - self._skipped_seen
+        self._skipped_seen = skipped
+        self.loss_scale = self._scale_used * 0.5
+        return True
 
     def _scale_for(self, numel):
         return float(self.loss_scale) if self.loss_scale is not None else numel / (2.0 * self.LOSS_SCALE_DIV)
@@ -708,10 +755,19 @@ class FinetuneTrainer:
     # all but the last one overlap the remaining ControlNet backward.  1/world is folded into the AdamW kernel.
     def gradient_buckets(self):
         """{stage: [(offset, numel)]}: contiguous flat-buffer ranges whose gradients are final when the backward reaches
-        the stage; "final" is the rest (input_blocks.0-2, zero-convs, time-embedding MLP, middle_block_out)."""
-        stage_of = lambda n: ("middle" if n.startswith("middle_block.") else
-                              next((st for b0, st in ((9, "ib9"), (6, "ib6"), (3, "ib3"))
-                                    if n.startswith("input_blocks.") and b0 <= int(n.split(".")[1]) < b0 + 3), "final"))
+        the stage (a block's zero-conv travels with its block); "final" is the rest: input_blocks.0-2 with their zero-convs and
+        the time-embedding MLP -- ~4 M of the 36.9 M elements, the only part whose all-reduce cannot overlap the backward."""
+        def stage_of(n):
+            # zero_convs.i is differentiated right before input_blocks.i, middle_block_out right before middle_block
+            if n.startswith(("middle_block.", "middle_block_out.")):
+                return "middle"
+            if n.startswith(("input_blocks.", "zero_convs.")):
+                i = int(n.split(".")[1])
+                for b0, st in ((9, "ib9"), (6, "ib6"), (3, "ib3")):
+                    if b0 <= i < b0 + 3:
+                        return st
+            return "final"
+
         buckets = {k: [] for k in ("middle", "ib9", "ib6", "ib3", "final")}
         for name in self.G.names:
             off, n = self.G.offsets[name]
@@ -721,6 +777,46 @@ class FinetuneTrainer:
             else:
                 r.append((off, n))
         return buckets
+
+    def _overlap(self):
+        return bool(self._cuts())
+
+    def _cuts(self):
+        """Backward stages after which a gradient bucket is closed and its all-reduce started (CTRLORA_ALLREDUCE_CUTS, comma
+        separated subset of middle,ib9,ib6,ib3; empty = one all-reduce after the backward).  Default: EMPTY.  Measured on
+        8 x B200 (profiles/r2_scaling_experiments.txt): no cut 74.77 ms/step, one cut after input_blocks.3 (89 % of the
+        buffer reduced under the three 64x64 blocks' backward) 75.07 ms, all four cuts 75.14 ms -- every cut splits the CUDA
+        graph, and NCCL's CTAs take SMs away from the persistent one-CTA-per-SM GEMMs they overlap with, which costs more
+        than the ~1 ms of all-reduce it hides.  The machinery stays for longer collectives (more ranks, multi-node)."""
+        import os
+        cuts = getattr(self, "allreduce_cuts", None)
+        if cuts is None:
+            cuts = os.environ.get("CTRLORA_ALLREDUCE_CUTS", "")
+        if isinstance(cuts, str):
+            cuts = [c for c in cuts.split(",") if c]
+        return [c for c in ("middle", "ib9", "ib6", "ib3") if c in cuts]
+
+    def merged_buckets(self):
+        """[(stage, ranges)] in backward order for the active cuts + ("final", ranges): buckets of skipped stages are merged
+        into the next active cut."""
+        def coalesce(ranges):
+            out = []
+            for off, n in sorted(ranges):
+                if out and out[-1][0] + out[-1][1] == off:
+                    out[-1] = (out[-1][0], out[-1][1] + n)
+                else:
+                    out.append((off, n))
+            return out
+
+        b = self.gradient_buckets()
+        cuts, out, pending = self._cuts(), [], []
+        for st in ("middle", "ib9", "ib6", "ib3"):
+            pending += b[st]
+            if st in cuts:
+                out.append((st, coalesce(pending)))
+                pending = []
+        out.append(("final", coalesce(pending + b["final"])))
+        return out
 
     def _reduce_ranges(self, ranges):
         """all-reduce `ranges` on the communication stream once everything enqueued so far on the compute stream is done"""
@@ -756,10 +852,11 @@ class FinetuneTrainer:
         torch.cuda.synchronize()
         prepare.bump_train_version()  # force the trainable-weight preparation into the captured region
         self._segments = None
-        if self.world > 1 and getattr(self, "overlap_allreduce", True):
+        if self.world > 1 and self._overlap():
             # one graph per gradient bucket, sharing a memory pool: replay k, start bucket k's all-reduce on the
             # communication stream, replay k+1 ...  (NCCL stays outside the captures)
-            buckets = self.gradient_buckets()
+            merged = self.merged_buckets()
+            buckets = dict(merged)
             segs, state = [], {}
             stream = torch.cuda.Stream()
             stream.wait_stream(cur)
@@ -768,6 +865,8 @@ class FinetuneTrainer:
                 state["g"].capture_begin()
 
                 def on_stage(name):
+                    if name not in buckets:
+                        return  # not an active cut
                     state["g"].capture_end()
                     segs.append((state["g"], buckets[name]))
                     state["g"] = torch.cuda.CUDAGraph()
@@ -806,9 +905,9 @@ class FinetuneTrainer:
         if getattr(self, "_graph", None) is not None:
             loss = self.loss_and_grads_graphed(x0, hint_latent, context, t, noise)
             overlapped = bool(self._segments)
-        elif self.world > 1 and getattr(self, "overlap_allreduce", True):
-            buckets = self.gradient_buckets()
-            self._on_stage = lambda name: self._reduce_ranges(buckets[name])
+        elif self.world > 1 and self._overlap():
+            buckets = dict(self.merged_buckets())
+            self._on_stage = lambda name: self._reduce_ranges(buckets.get(name))
             try:
                 loss = self.loss_and_grads(x0, hint_latent, context, t, noise)
             finally:
@@ -822,17 +921,17 @@ class FinetuneTrainer:
         else:
             self.reduce_gradients()
         ops.nonfinite_flag(self.G.flat_g, self.overflow_flag)  # after the all-reduce: every rank takes the same decision
-        self.step_count += 1
-        ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, self.step_count, lr=self.lr,
+        step_dev, bc = self._seg_state("all")
+        ops.adamw_begin(step_dev, self.overflow_flag, self.betas, bc, self._skipped_dev)
+        ops.adamw_step(self.G.flat_p, self.G.flat_g, self.G.exp_avg, self.G.exp_avg_sq, 0, lr=self.lr,
                        betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                       grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag)
+                       grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag, bc_dev=bc)
         prepare.bump_train_version()
-        if self.dynamic_loss_scale and self.step_count % self.CHECK_OVERFLOW_EVERY == 0 and self._overflowed():
-            # GradScaler semantics: the update was skipped on the device; halve the scale (re-capturing the graph, whose
-            # loss kernel has the scale baked in) and do not count the step
-            self.step_count -= 1
-            self.skipped_steps += 1
-            self.loss_scale = self._scale_used * 0.5
+        self.step_count += 1
+        if self._poll_overflow():
+            # GradScaler semantics: the updates were skipped on the device; the scale is halved (re-capturing the graph, whose
+            # loss kernel has the scale baked in)
+            self.step_count = int(step_dev.item())
             if getattr(self, "_graph", None) is not None:
                 self.capture(*self._static, warmup=1)
         return loss
@@ -904,6 +1003,7 @@ class PretrainTrainer(FinetuneTrainer):
         self.loss_scale, self.dynamic_loss_scale = loss_scale, dynamic_loss_scale
         self.overflow_flag = torch.zeros(1, device=self.G.flat_p.device, dtype=torch.int32)
         self.skipped_steps = 0
+        self._init_step_state(self.G.flat_p.device)
         self._graphs, self._pool, self._static, self._static_loss = {}, None, None, {}
         self.task = self.tasks[0] if self.tasks else None
 
@@ -973,21 +1073,19 @@ class PretrainTrainer(FinetuneTrainer):
         self.reduce_gradients(segs)
         for off, n, _ in segs:
             ops.nonfinite_flag(self.G.flat_g[off:off + n], self.overflow_flag)
-        self.step_count += 1
         G = self.G
-        for off, n, key in segs:
-            k = self.seg_steps.get(key, 0) + 1
-            self.seg_steps[key] = k
-            ops.adamw_step(G.flat_p[off:off + n], G.flat_g[off:off + n], G.exp_avg[off:off + n], G.exp_avg_sq[off:off + n], k,
+        for i, (off, n, key) in enumerate(segs):
+            step_dev, bc = self._seg_state(key)
+            ops.adamw_begin(step_dev, self.overflow_flag, self.betas, bc, self._skipped_dev if i == 0 else None)
+            ops.adamw_step(G.flat_p[off:off + n], G.flat_g[off:off + n], G.exp_avg[off:off + n], G.exp_avg_sq[off:off + n], 0,
                            lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                           grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag)
+                           grad_scale=1.0 / (self.world * self._scale_used), skip_flag=self.overflow_flag, bc_dev=bc)
+            self.seg_steps[key] = self.seg_steps.get(key, 0) + 1
         prepare.bump_train_version()
-        if self.dynamic_loss_scale and self._overflowed():
-            self.step_count -= 1
-            for _, _, key in segs:
-                self.seg_steps[key] -= 1
-            self.skipped_steps += 1
-            self.loss_scale = self._scale_used * 0.5
+        self.step_count += 1
+        if self._poll_overflow():
+            self.seg_steps = {k: int(v.item()) for k, v in self._step_dev.items()}
+            self.step_count = self.seg_steps.get("base", self.step_count)
             if self._graphs:
                 tasks = list(self._graphs)
                 self._graphs.clear()

@@ -29,6 +29,9 @@ int ctrlora_abi_version(void);
 /* Last CUDA error string seen by this library on the calling thread's device (host pointer, static storage). */
 const char* ctrlora_last_cuda_error(void);
 
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: a memset node, not a kernel (zero-initialised key padding of V^T etc.) */
+int ctrlora_memset_zero(void* ptr, long long bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Implicit GEMM on the 5th-gen tensor cores (tcgen05, accumulators in TMEM, operands staged by TMA):
  *   out[m, n] = epilogue( sum_{tap, c} A[pixel(m) + tap_offset, c] * W[n, tap, c]  (+ sum_c A2[pixel(m), c] * W2[n, c]) )
@@ -236,7 +239,12 @@ int ctrlora_mse_loss_grad(const float* eps, const float* noise, float* loss, voi
  * skip_flag (device int, may be NULL): when non-zero the step is skipped (loss-scale overflow, see below). */
 int ctrlora_adamw_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int step, float grad_scale, const int* skip_flag,
+                      const float* bc_dev /* optional device {1-beta1^step, 1-beta2^step} from ctrlora_adamw_begin; then `step`
+                                             is ignored */,
                       void* stream);
+/* In front of an AdamW step: ++*step_counter unless *skip_flag (then ++*skipped), bc[0..1] = 1 - beta^step.  Keeps torch's
+ * per-parameter `step` semantics (skipped steps do not count) without a host read of the overflow flag every step. */
+int ctrlora_adamw_begin(int* step_counter, const int* skip_flag, float beta1, float beta2, float* bc, int* skipped, void* stream);
 /* *flag |= 1 if any element of x is NaN/Inf: the overflow check of the loss-scaled fp16 backward (the reference trains in
  * fp32 and has no such step; torch.cuda.amp.GradScaler semantics: skip the update, lower the scale). */
 int ctrlora_nonfinite_flag_f32(const float* x, long long n, int* flag, void* stream);

@@ -171,3 +171,41 @@ def test_graph_follows_load_state_dict(g):
     # is ~1e-3 (tools/debug_determinism.py)
     assert rel(x2, x3) < 5e-3, "graph replayed stale weights"
     assert rel(x2, x1) > 5e-2
+
+
+def test_context_cache_follows_prompt_changes(g):
+    """The sampler registers the text context as step-invariant (K / V^T projected once per run): a new prompt through the SAME
+    sampler / graph, and in-place edits of the context tensor, must be seen; a call that bypasses the sampler must not hit a
+    stale cache."""
+    from cldm.ddim_hacked import DDIMSampler
+    from oracle import synth
+    gt = torch.load(os.path.join(GOLD, "tiny_finetune_golden.pt"), weights_only=False)
+    model = build("finetune", g, gt["control_shapes"])
+    d = inputs(g)
+    B = g["B"]
+    ts = torch.full((B,), 981, dtype=torch.long, device="cuda")
+    ctx2 = synth.synth_input("ctx_other", (B, 77, 64), g["seed"]).cuda()
+    s = DDIMSampler(model, use_cuda_graph=True)
+    s.make_schedule(50, ddim_eta=0.0, verbose=False)
+    eager = DDIMSampler(model, use_cuda_graph=False, batched_cfg=False)
+    eager.make_schedule(50, ddim_eta=0.0, verbose=False)
+
+    def run(smp, ctx, uc):
+        cond = {"c_crossattn": [ctx], "c_concat": [d["hint"]]}
+        ucond = {"c_crossattn": [uc], "c_concat": [d["hint"]]}
+        with smp.run_mode():  # what sample() does: conditioning constant over the run -> context K / V^T cached
+            out = smp.p_sample_ddim(d["x"], cond, ts, index=49, unconditional_guidance_scale=7.5, unconditional_conditioning=ucond)[0]
+            out2 = smp.p_sample_ddim(d["x"], cond, ts, index=49, unconditional_guidance_scale=7.5, unconditional_conditioning=ucond)[0]
+        assert torch.equal(out, out2)  # second step of the run: cache hit, bit-identical (the forward is deterministic)
+        return out.clone()
+
+    a1 = run(s, d["ctx"], d["uc"])
+    a2 = run(s, ctx2, d["uc"])              # new prompt, same sampler and graph
+    ctx3 = d["ctx"].clone()
+    a3 = run(s, ctx3, d["uc"])
+    ctx3.mul_(0.5)                          # in-place edit of a registered context
+    a4 = run(s, ctx3, d["uc"])
+    for got, ctx in ((a1, d["ctx"]), (a2, ctx2), (a3, d["ctx"]), (a4, d["ctx"] * 0.5)):
+        ref = run(eager, ctx.clone(), d["uc"].clone())
+        assert rel(got, ref) < 1e-5, rel(got, ref)
+    assert rel(a2, a1) > 1e-3 and rel(a4, a3) > 1e-3

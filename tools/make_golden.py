@@ -409,6 +409,40 @@ def vae(seed=0, full=False):
     print("wrote", out, os.path.getsize(out) // 1024, "KiB")
 
 
+def ranks(seed=0):
+    """BASELINE.json configs[4] (LoRA rank sweep) at the tiny config: the finetune training step of the reference for LoRA
+    ranks 4 (not a multiple of 8: exercises the rank padding of the fold / gradient GEMMs), 16 and 32 -- eps, loss, all 246
+    gradient norms."""
+    base = open(os.path.join(GOLD, "tiny_finetune.yaml")).read()
+    B, H = 2, 16
+    x = synth.synth_input("x", (B, 4, H, H), seed)
+    hint = synth.synth_input("hint", (B, 4, H, H), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 64), seed)
+    noise = synth.synth_input("noise", (B, 4, H, H), seed)
+    t = torch.tensor([981, 21], dtype=torch.long)
+    g = {"seed": seed, "B": B, "H": H, "t": t, "ranks": {}}
+    for r in (4, 16, 32):
+        path = os.path.join("/tmp", f"tiny_rank{r}.yaml")
+        with open(path, "w") as f:
+            f.write(base.replace("lora_rank: 8", f"lora_rank: {r}"))
+        model = build_reference(path, seed)
+        model.encode_first_stage = lambda h: h
+        model.get_first_stage_encoding = lambda h: h
+        x_noisy = model.q_sample(x_start=x, t=t, noise=noise)
+        eps = model.apply_model(x_noisy, t, {"c_crossattn": [ctx], "c_concat": [hint]})
+        loss = model.get_loss(eps, noise, mean=False).mean([1, 2, 3]).mean()
+        loss.backward()
+        names = [n for n, _ in model.control_model.named_parameters()
+                 if "lora_layer" in n or "zero_convs" in n or "middle_block_out" in n or "norm" in n]
+        gr = dict(model.control_model.named_parameters())
+        g["ranks"][r] = {"control_shapes": shapes_of(model.control_model), "eps": eps.detach().clone(), "loss": loss.detach().clone(),
+                         "grad_norms": {n: gr[n].grad.norm().item() for n in names}}
+        g["unet_shapes"] = shapes_of(model.model.diffusion_model)
+    out = os.path.join(GOLD, "tiny_ranks_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
 def schedule():
     """Task order produced by the reference's BatchSchedulerSampler for seeded np.random (tests/test_scheduler_cpu.py)."""
     import json
@@ -453,6 +487,7 @@ if __name__ == "__main__":
     ap.add_argument("--variants", action="store_true")
     ap.add_argument("--full-train", action="store_true")
     ap.add_argument("--schedule", action="store_true")
+    ap.add_argument("--ranks", action="store_true")
     ap.add_argument("--vae", action="store_true")
     ap.add_argument("--vae-full", action="store_true")
     a = ap.parse_args()
@@ -465,6 +500,8 @@ if __name__ == "__main__":
         full_train()
     elif a.schedule:
         schedule()
+    elif a.ranks:
+        ranks()
     elif a.vae:
         vae()
     elif a.vae_full:
