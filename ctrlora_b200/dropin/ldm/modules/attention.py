@@ -68,14 +68,15 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
         self._prep = prepare.PrepCache()
 
-    def run(self, x2d, residual=None):
+    def run(self, x2d, residual=None, out=None):
         """x2d fp16 [M, dim] -> fp16 [M, dim_out] (+ residual)."""
+        out_buf = out
         proj, out = self.net[0].proj, self.net[2]
         lk = prepare.lora_key
         w1 = self._prep.get(("w1", lk(proj)), prepare.linear_params(proj), lambda: prepare.effective_linear_weight(proj))
         w2 = self._prep.get(("w2", lk(out)), prepare.linear_params(out), lambda: prepare.effective_linear_weight(out))
         g = ops.gemm(x2d, w1, bias=prepare.bias_f32(proj.bias), geglu=True)
-        return ops.gemm(g, w2, bias=prepare.bias_f32(out.bias), residual=residual)
+        return ops.gemm(g, w2, bias=prepare.bias_f32(out.bias), residual=residual, out=out_buf)
 
     def forward(self, x):
         shp = x.shape
@@ -195,12 +196,12 @@ class BasicTransformerBlock(nn.Module):
         norm = prepare.effective(norm)
         return ops.layernorm(x2d, prepare.bias_f32(norm.weight), prepare.bias_f32(norm.bias), norm.eps)
 
-    def run(self, x2d, batch, n, ctx2d, nk):
-        """x2d fp16 [batch*n, dim] -> same shape (reference _forward :271-275)."""
+    def run(self, x2d, batch, n, ctx2d, nk, out=None):
+        """x2d fp16 [batch*n, dim] -> same shape (reference _forward :271-275); `out`: optional destination buffer."""
         c1 = (ctx2d, nk) if self.disable_self_attn else (None, None)
         x2d = self.attn1.run(self._ln(self.norm1, x2d), batch, n, c1[0], c1[1], residual=x2d)
         x2d = self.attn2.run(self._ln(self.norm2, x2d), batch, n, ctx2d, nk, residual=x2d)
-        return self.ff.run(self._ln(self.norm3, x2d), residual=x2d)
+        return self.ff.run(self._ln(self.norm3, x2d), residual=x2d, out=out)
 
     def forward(self, x, context=None):
         b, n, _ = x.shape
@@ -236,6 +237,39 @@ class SpatialTransformer(nn.Module):
             return self._prep.get((key, prepare.lora_key(mod)), prepare.linear_params(mod),
                                   lambda: prepare.effective_linear_weight(mod))
         return self._prep.get(key, [mod.weight], lambda: prepare.conv_weight(mod.weight))
+
+    def forward_grouped(self, x, context, n_groups, attach):
+        """One pass over a batch made of `n_groups` equal slices that use DIFFERENT LoRA / norm sets (multi-LoRA inference,
+        cldm/cldm_ctrlora_inference.py:156-178 runs the ControlNet once per set): `attach(self, g)` re-points this module's
+        LoRA layers and switchable norms to set g.  The 1x1 convs (no LoRA) run once over the whole batch; the GroupNorm and
+        the transformer blocks run per slice, writing into shared buffers (no concatenation)."""
+        xp = pixel_major(x)
+        b, h, w, c = xp.shape
+        bg = b // n_groups
+        if not isinstance(context, list):
+            context = [context]
+        xn = torch.empty_like(xp)
+        for g in range(n_groups):
+            attach(self, g)
+            gn = prepare.effective(self.norm)
+            ops.groupnorm(xp[g * bg:(g + 1) * bg], prepare.bias_f32(gn.weight), prepare.bias_f32(gn.bias), gn.eps, False,
+                          groups=gn.num_groups, out=xn[g * bg:(g + 1) * bg])
+        y = ops.gemm(xn, self._w("in", self.proj_in), bias=prepare.bias_f32(self.proj_in.bias))
+        y2d = y.view(b * h * w, -1)
+        rows = bg * h * w
+        y_out = torch.empty_like(y2d)
+        for g in range(n_groups):
+            attach(self, g)
+            yg = y2d[g * rows:(g + 1) * rows]
+            for i, block in enumerate(self.transformer_blocks):
+                ctx = context[i] if i < len(context) else context[-1]
+                ctx_g = None if ctx is None else (ctx if ctx.shape[0] == bg else ctx[g * bg:(g + 1) * bg])  # shared or per slice
+                ctx2d, nk = (None, None) if ctx_g is None else (to_f16_rows(ctx_g), ctx_g.shape[1])
+                last = i == len(self.transformer_blocks) - 1
+                yg = block.run(yg, bg, h * w, ctx2d, nk, out=y_out[g * rows:(g + 1) * rows] if last else None)
+        out = ops.gemm(y_out.view(b, h, w, -1), self._w("out", self.proj_out), bias=prepare.bias_f32(self.proj_out.bias),
+                       residual=xp.view(b * h * w, c))
+        return nchw_view(out)
 
     def forward(self, x, context=None):
         xp = pixel_major(x)  # [B, H, W, C]

@@ -310,23 +310,24 @@ class UNetModel(nn.Module):
     def _resblocks(self):
         return [m for m in self.modules() if isinstance(m, ResBlock)]
 
-    def embed(self, timesteps):
+    def embed(self, timesteps, out_raw=None, out_all=None):
         """timestep_embedding -> time_embed MLP -> every ResBlock's emb_layers, as three launches (reference: one
-        Linear per ResBlock, openaimodel.py:263; the ControlNet's are LoRA-wrapped, cldm_ctrlora_finetune.py:21-38)."""
+        Linear per ResBlock, openaimodel.py:263; the ControlNet's are LoRA-wrapped, cldm_ctrlora_finetune.py:21-38).
+        out_raw / out_all: optional fp32 destination rows ([B, 1280] / [B, sum Cout], row strides free)."""
         f32 = prepare.bias_f32
         t_emb = timestep_embedding(timesteps, self.model_channels)
         l0, l2 = self.time_embed[0], self.time_embed[2]
         w0 = self._prep.get("te0", prepare.linear_params(l0), lambda: prepare.effective_linear_weight(l0).view(l0.out_features, -1))
         w2 = self._prep.get("te2", prepare.linear_params(l2), lambda: prepare.effective_linear_weight(l2).view(l2.out_features, -1))
         hid = ops.small_linear(t_emb, w0, f32(l0.bias), silu_out=True)
-        emb = ops.small_linear(hid, w2, f32(l2.bias))
+        emb = ops.small_linear(hid, w2, f32(l2.bias), out=out_raw)
         blocks = self._resblocks()
         lins = [b.emb_layers[1] for b in blocks]
         params = [p for lin in lins for p in prepare.linear_params(lin)] + [lin.bias for lin in lins]
         wcat, bcat = self._prep.get("emb_cat", params, lambda: (
             torch.cat([b.emb_weight() for b in blocks], 0).contiguous(),
             torch.cat([lin.bias.detach().float() for lin in lins], 0).contiguous()))
-        allout = ops.small_linear(emb, wcat, bcat, silu_in=True)  # [B, sum Cout]
+        allout = ops.small_linear(emb, wcat, bcat, silu_in=True, out=out_all)  # [B, sum Cout]
         slices, off = {}, 0
         for b in blocks:
             slices[id(b)] = allout[:, off:off + b.out_channels]

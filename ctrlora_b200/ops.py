@@ -297,7 +297,7 @@ def _gn_partial_buffers(device):
 
 
 def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None, add2=None, add2_scale=1.0,
-              groups=32, want_raw=False, stats_ws=None, want_stats=False):
+              groups=32, want_raw=False, stats_ws=None, want_stats=False, out=None):
     """GroupNorm(+SiLU) over [x1 (+s1*add1) | x2 (+s2*add2)], pixel-major fp16 [B,H,W,C*]; returns y (and raw concat)."""
     _require_cuda(x1, x2, add1, add2)
     b, h, w, c1, ld1 = _as_bhwc(x1)
@@ -309,7 +309,8 @@ def groupnorm(x1, gamma, beta, eps, silu, *, add1=None, add1_scale=1.0, x2=None,
         if ad is not None:
             assert ad.shape == ref.shape and ad.stride() == ref.stride() and ad.dtype == torch.float16
     ctot = c1 + c2
-    y = torch.empty((b, h, w, ctot), device=x1.device, dtype=torch.float16)
+    y = torch.empty((b, h, w, ctot), device=x1.device, dtype=torch.float16) if out is None else out
+    assert y.shape == (b, h, w, ctot) and y.is_contiguous() and y.dtype == torch.float16
     raw = torch.empty_like(y) if want_raw else None
     prezeroed = 0
     if stats_ws is None:
@@ -364,13 +365,14 @@ def attention(q, k, vt, batch, heads, nq, nk, head_dim, out=None, lse=None):
     return out
 
 
-def nchw_to_nhwc_f16(x, c_pad=None):
+def nchw_to_nhwc_f16(x, c_pad=None, out=None):
     """fp32 [B,C,H,W] contiguous -> fp16 [B,H,W,c_pad] (zero-padded channels)."""
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
     b, c, h, w = x.shape
     c_pad = c_pad or c
-    y = torch.empty((b, h, w, c_pad), device=x.device, dtype=torch.float16)
+    y = torch.empty((b, h, w, c_pad), device=x.device, dtype=torch.float16) if out is None else out
+    assert y.shape == (b, h, w, c_pad) and y.is_contiguous() and y.dtype == torch.float16
     _count(1)
     check(_lib.load().ctrlora_nchw_f32_to_nhwc_f16(_dp(x), _dp(y), b, c, h * w, c_pad, _sp()), "nchw_to_nhwc")
     return y

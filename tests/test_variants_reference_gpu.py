@@ -78,7 +78,12 @@ def test_inference_apply_model_weighted_sum_vs_reference(g):
         e_def = rel(model.apply_model(d["x"], d["t"], conds), g["inference_eps_default"])
         model.lora_weights = [0.7, 0.3]
         model.control_scales = [0.5 + 0.1 * i for i in range(13)]
-        e_w = rel(model.apply_model(d["x"], d["t"], conds), g["inference_eps_weighted"])
+        eps_grouped = model.apply_model(d["x"], d["t"], conds)   # default: both LoRA sets in ONE ControlNet pass
+        e_w = rel(eps_grouped, g["inference_eps_weighted"])
+        model.grouped_multi_lora = False                          # the reference's loop: one ControlNet pass per set
+        eps_seq = model.apply_model(d["x"], d["t"], conds)
+        model.grouped_multi_lora = True
+        assert torch.equal(eps_grouped, eps_seq), rel(eps_grouped, eps_seq)  # same kernels per image: bit-identical
         model.control_scales = [1.0] * 13
         cerr = []
         for i in (0, 1):
