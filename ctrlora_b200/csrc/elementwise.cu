@@ -204,6 +204,59 @@ __global__ void transpose_f16_kernel(const __half* __restrict__ src, __half* __r
     dst[i] = src[(b * R + r) * C + c];
 }
 
+// ---- tiled fp16 transpose with free outer strides: dst[z', j, i] = src[z, i, j], 64 x 64 tiles through shared memory,
+// 128-byte row segments on both sides.  z' = Z-1-z when `flip` (the tap reversal of a convolution's data-gradient weight).
+__device__ __forceinline__ __half2 load_pair(const __half* p) { return *reinterpret_cast<const __half2*>(p); }
+__device__ __forceinline__ __half2 load_pair(const float* p) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    return __floats2half2_rn(v.x, v.y);
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256)
+tiled_transpose_f16_kernel(const S* __restrict__ src, __half* __restrict__ dst, int I, int J, long long s_i,
+                           long long d_j, long long src_z, long long dst_z, int flip) {
+    __shared__ __half tile[64][66];
+    const int z = blockIdx.z, zo = flip ? static_cast<int>(gridDim.z) - 1 - z : z;
+    src += z * src_z;
+    dst += zo * dst_z;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = i0 + ty + 8 * k, j = j0 + 2 * tx;
+        __half2 v = __floats2half2_rn(0.f, 0.f);
+        if (i < I && j < J) v = load_pair(src + i * s_i + j);
+        tile[ty + 8 * k][2 * tx] = __low2half(v);
+        tile[ty + 8 * k][2 * tx + 1] = __high2half(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int j = j0 + ty + 8 * k, i = i0 + 2 * tx;
+        if (j < J && i < I)
+            *reinterpret_cast<__half2*>(dst + j * d_j + i) = __halves2half2(tile[2 * tx][ty + 8 * k], tile[2 * tx + 1][ty + 8 * k]);
+    }
+}
+
+static bool tiled_transpose_ok(const void* src, const void* dst, int I, int J, long long s_i, long long d_j, long long src_z,
+                               long long dst_z, long long Z, int src_align = 3) {
+    return !((I | J) & 1) && !((s_i | d_j | src_z | dst_z) & 1) && Z <= 65535 && (J + 63) / 64 > 0 && (I + 63) / 64 <= 65535 &&
+           !(reinterpret_cast<uintptr_t>(src) & src_align) && !(reinterpret_cast<uintptr_t>(dst) & 3);
+}
+
+// fp32 -> fp16 plain cast, 8 elements per thread (the per-step fp16 copies of the trainable fp32 master weights)
+__global__ void __launch_bounds__(256) cast_vec8_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long vecs) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= vecs) return;
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    __half2* h = reinterpret_cast<__half2*>(&o);
+    h[0] = __floats2half2_rn(a.x, a.y); h[1] = __floats2half2_rn(a.z, a.w);
+    h[2] = __floats2half2_rn(b.x, b.y); h[3] = __floats2half2_rn(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+}
+
 // ---- DDIM update, one pass: CFG combine + pred_x0 + x_prev; explicit round-to-nearest ops in the reference's
 // order (cldm/ddim_hacked.py:192,215,226-230) so that no FMA contraction changes the fp32 results.
 // stats[b] += sum(x_prev^2) of image b (warp-reduced), a per-step scalar the host can read back.
@@ -315,10 +368,39 @@ __global__ void __launch_bounds__(256)
 small_linear_staged_kernel(const float* __restrict__ x, int ldx, const __half* __restrict__ w, const float* __restrict__ bias,
                            float* __restrict__ y, int ldy, int rows, int N, int K, int silu_in, int silu_out, int groups_per_warp) {
     extern __shared__ float sx[];  // [rows][K]
-    for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
-        const int r = i / K, k = i - r * K;
-        const float v = x[static_cast<long long>(r) * ldx + k];
-        sx[i] = silu_in ? silu_f(v) : v;
+    {
+        // staging: 16-byte loads, four in flight per thread (the scalar one-load-per-iteration loop of round 1 was a chain of
+        // dependent global-load latencies: 20-40 us for 16 x 1280 activations, most of this kernel's time)
+        const int k4 = K >> 2, total4 = rows * k4;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+        int i = threadIdx.x;
+        if (vec_ok) {
+            for (; i + 3 * static_cast<int>(blockDim.x) < total4; i += 4 * blockDim.x) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = i + u * blockDim.x, r = j / k4, c = j - r * k4;
+                    v[u] = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + 4 * c);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (silu_in) { v[u].x = silu_f(v[u].x); v[u].y = silu_f(v[u].y); v[u].z = silu_f(v[u].z); v[u].w = silu_f(v[u].w); }
+                    *reinterpret_cast<float4*>(sx + 4 * (i + u * blockDim.x)) = v[u];
+                }
+            }
+            for (; i < total4; i += blockDim.x) {
+                const int r = i / k4, c = i - r * k4;
+                float4 v = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + 4 * c);
+                if (silu_in) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                *reinterpret_cast<float4*>(sx + 4 * i) = v;
+            }
+        } else {
+            for (int e = threadIdx.x; e < rows * K; e += blockDim.x) {
+                const int r = e / K, k = e - r * K;
+                const float v = x[static_cast<long long>(r) * ldx + k];
+                sx[e] = silu_in ? silu_f(v) : v;
+            }
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -459,12 +541,41 @@ extern "C" int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, lo
                                                  void* stream) {
     if (!src || !dst) return CTRLORA_ERR_ARG;
     const long long total = batch * rows * cols;
+    if (total <= 0) return CTRLORA_OK;
+    const bool aligned = !(reinterpret_cast<uintptr_t>(src) & 15) && !(reinterpret_cast<uintptr_t>(dst) & 15);
+    if ((rows == 1 || cols == 1) && total % 8 == 0 && aligned) {
+        cast_vec8_kernel<<<blocks_for(total / 8, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__half*>(dst), total / 8);
+        return LAUNCH_OK();
+    }
+    if (rows > 1 && cols > 1 &&
+        tiled_transpose_ok(src, dst, rows, cols, cols, rows, (long long)rows * cols, (long long)rows * cols, batch, 7)) {
+        tiled_transpose_f16_kernel<float><<<dim3((cols + 63) / 64, (rows + 63) / 64, (unsigned)batch), 256, 0, STREAM(stream)>>>(
+            src, reinterpret_cast<__half*>(dst), rows, cols, cols, rows, (long long)rows * cols, (long long)rows * cols, 0);
+        return LAUNCH_OK();
+    }
     cast_transpose_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<__half*>(dst), batch,
                                                                             rows, cols);
     return LAUNCH_OK();
 }
 
+// conv kernel weight [Cout, taps, Cin] -> data-gradient weight [Cin, taps reversed, Cout]  (dx = conv(dy, W_d), same padding)
+extern "C" int ctrlora_conv_dgrad_weight_f16(const void* src, void* dst, int cout, int taps, int cin, void* stream) {
+    if (!src || !dst || cout <= 0 || taps <= 0 || cin <= 0) return CTRLORA_ERR_ARG;
+    if (!tiled_transpose_ok(src, dst, cout, cin, (long long)taps * cin, (long long)taps * cout, cin, cout, taps)) return CTRLORA_ERR_ARG;
+    tiled_transpose_f16_kernel<__half><<<dim3((cin + 63) / 64, (cout + 63) / 64, taps), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), cout, cin, (long long)taps * cin,
+        (long long)taps * cout, cin, cout, 1);
+    return LAUNCH_OK();
+}
+
 extern "C" int ctrlora_transpose_f16(const void* src, void* dst, long long batch, int rows, int cols, void* stream) {
+    if (src && dst && tiled_transpose_ok(src, dst, rows, cols, cols, rows, (long long)rows * cols, (long long)rows * cols, batch) &&
+        batch > 0) {
+        tiled_transpose_f16_kernel<__half><<<dim3((cols + 63) / 64, (rows + 63) / 64, (unsigned)batch), 256, 0, STREAM(stream)>>>(
+            reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), rows, cols, cols, rows,
+            (long long)rows * cols, (long long)rows * cols, 0);
+        return LAUNCH_OK();
+    }
     if (!src || !dst) return CTRLORA_ERR_ARG;
     const long long total = batch * rows * cols;
     transpose_f16_kernel<<<blocks_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<const __half*>(src),

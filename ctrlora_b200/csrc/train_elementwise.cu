@@ -75,6 +75,60 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long r
     atomicAdd(&out[c], scale * acc);
 }
 
+// fp16 rows of 8-column vectors: block (32 vectors, 8 row lanes), 16-byte loads four rows deep, row lanes combined in
+// shared memory, one atomic per column per block
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const __half* __restrict__ x, long long ld, long long rows, int vecs, float scale, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float red[8][32][9];
+    const int vx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + vx;
+    const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+    const long long r0 = static_cast<long long>(blockIdx.y) * chunk, r1 = min(rows, r0 + chunk);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (v < vecs) {
+        const __half* base = x + 8 * v;
+        long long r = r0 + ry;
+        for (; r + 24 < r1; r += 32) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(base + (r + 8 * u) * ld);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&q[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(base + r * ld);
+            const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[ry][vx][j] = acc[j];
+    __syncthreads();
+    // 256 threads = 32 vectors x 8 columns
+    const int col = threadIdx.x & 7, vec = threadIdx.x >> 3;
+    const int vo = blockIdx.x * 32 + vec;
+    if (vo >= vecs) return;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][vec][col];
+    atomicAdd(&out[8 * vo + col], scale * t);
+}
+
 // per-image column sums: out[img, c] = sum over the image's rows (time-embedding gradient of a ResBlock conv)
 __global__ void rowgroup_colsum_kernel(const __half* __restrict__ x, long long ld, int rows_per_img, int cols, float* __restrict__ out,
                                        long long ldo) {
@@ -341,6 +395,15 @@ extern "C" int ctrlora_geglu_bwd_f16(const void* h, const void* dout, void* dh, 
 extern "C" int ctrlora_colsum(const void* x, int x_is_f32, long long ld, long long rows, int cols, float scale, float* out,
                               void* stream) {
     if (!x || !out) return CTRLORA_ERR_ARG;
+    if (!x_is_f32 && cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int vecs = cols / 8, xb = (vecs + 31) / 32;
+        long long ys = (2 * 148 + xb - 1) / xb;  // about two blocks per SM
+        if (ys > rows / 64) ys = rows / 64;
+        if (ys < 1) ys = 1;
+        launch_pdl(colsum_vec_kernel, dim3(xb, (unsigned)ys), dim3(256), (size_t)0, STREAM(stream),
+                   reinterpret_cast<const __half*>(x), ld, rows, vecs, scale, out);
+        return LAUNCH_OK();
+    }
     int ysplit = static_cast<int>(rows / 256);
     if (ysplit < 1) ysplit = 1;
     if (ysplit > 64) ysplit = 64;

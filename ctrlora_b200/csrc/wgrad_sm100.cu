@@ -29,6 +29,12 @@ struct WgradParams {
     int stage_bytes, stages;
     uint32_t idesc;
     float* ws;         // [splits][P_pad][Q_pad] fp32, P_pad = p_tiles*128, Q_pad = q_tiles*q_tile
+    // direct mode (splits == 1: enough output tiles to fill the machine, e.g. the dense conv gradients of pretraining):
+    // the epilogue applies alpha / beta itself and writes the result row-major -- no workspace round trip, no reduce kernel
+    int direct;
+    float* out;
+    long long ldo;
+    float alpha, beta;
 };
 
 // MN-major operand, SWIZZLE_128B: 64-feature atoms (128 B rows), 8-token groups 1024 B apart (SBO), atoms `lbo` apart.
@@ -119,7 +125,49 @@ wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // slice layout [Q_pad / 4][P_pad rows][4 floats]: the 32 lanes (rows) of a warp write 512 contiguous bytes
         const long long P_pad = static_cast<long long>(p.p_tiles) * 128, Q_pad = static_cast<long long>(p.q_tiles) * p.q_tile;
         float* dst = p.ws + static_cast<long long>(split) * P_pad * Q_pad + (static_cast<long long>(q0 >> 2) * P_pad + p0 + r) * 4;
-        if (it1 > it0) {
+        if (p.direct) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
+            // every MMA has completed, so the operand ring is free: each epilogue warp transposes its 32 x 32 chunks through
+            // a [32][36]-float patch of it (16-byte accesses, conflict free both ways) and touches `out` as 128-byte row
+            // segments, four rows per instruction
+            float* patch = reinterpret_cast<float*>(smem) + lane_grp * (32 * 36);
+            const int sub_r = lane >> 3, c4 = lane & 7;
+            const int row_base = p0 + lane_grp * 32;
+            for (int c = 0; c < p.q_tile; c += 32) {
+                if (q0 + c >= p.Q) break;
+                uint32_t raw[32];
+                tmem_ld_32x32(t_row + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(patch + lane * 36 + 4 * q) =
+                        make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                                    __uint_as_float(raw[4 * q + 3]));
+                __syncwarp();
+                const int col = q0 + c + 4 * c4;
+                const bool col_ok = col < p.Q;  // Q % 8 == 0: a 4-vector is inside or outside
+                float4 o[8];
+                if (p.beta != 0.f) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row_base + 4 * it + sub_r;
+                        o[it] = (col_ok && row < p.P) ? *reinterpret_cast<const float4*>(p.out + row * p.ldo + col)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = row_base + 4 * it + sub_r;
+                    float4 v = *reinterpret_cast<const float4*>(patch + (4 * it + sub_r) * 36 + 4 * c4);
+                    v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+                    if (p.beta != 0.f) { v.x += p.beta * o[it].x; v.y += p.beta * o[it].y; v.z += p.beta * o[it].z; v.w += p.beta * o[it].w; }
+                    if (col_ok && row < p.P) *reinterpret_cast<float4*>(p.out + row * p.ldo + col) = v;
+                }
+                __syncwarp();
+            }
+        } else if (it1 > it0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16);
@@ -144,23 +192,35 @@ wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // out[p, q] = alpha * sum_s ws[s][p][q] + beta * out[p, q]   (fixed summation order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int P, int Q, int P_pad, int Q_pad,
-                                    int splits, long long ldo, float alpha, float beta) {
+// block = 32 rows x 32 columns: the slices are read rows-fastest (512 contiguous bytes per warp, the layout the GEMM
+// epilogue wrote), transposed through shared memory, and `out` is read/written as 128-byte row segments.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int P, int Q, int P_pad, int Q_pad,
+                    int splits, long long ldo, float alpha, float beta) {
     pdl_launch_dependents();
     pdl_wait();
-    // thread = (4 columns, row), rows fastest: the slice reads are 512 contiguous bytes per warp
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ float4 tile[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, c4_0 = blockIdx.y * 8;
     const int q4s = Q >> 2;  // Q is a multiple of 8
-    if (i >= static_cast<long long>(P) * q4s) return;
-    const int pr = static_cast<int>(i % P);
-    const int q4 = static_cast<int>(i / P);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long slice = static_cast<long long>(P_pad) * Q_pad;
-    const float* src = ws + (static_cast<long long>(q4) * P_pad + pr) * 4;
-    for (int s = 0; s < splits; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(src + s * slice);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int pr = r0 + tx, q4 = c4_0 + ty;
+        if (pr < P && q4 < q4s) {
+            const long long slice = static_cast<long long>(P_pad) * Q_pad;
+            const float* src = ws + (static_cast<long long>(q4) * P_pad + pr) * 4;
+            for (int s = 0; s < splits; ++s) {
+                const float4 v = *reinterpret_cast<const float4*>(src + s * slice);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        tile[ty][tx] = acc;
     }
+    __syncthreads();
+    const int row = threadIdx.x >> 3, c4 = threadIdx.x & 7;
+    const int pr = r0 + row, q4 = c4_0 + c4;
+    if (pr >= P || q4 >= q4s) return;
+    float4 acc = tile[c4][row];
     float* o = out + pr * ldo + 4 * q4;
     if (beta != 0.f) { acc.x = alpha * acc.x + beta * o[0]; acc.y = alpha * acc.y + beta * o[1]; acc.z = alpha * acc.z + beta * o[2]; acc.w = alpha * acc.w + beta * o[3]; }
     else { acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha; }
@@ -195,10 +255,15 @@ extern "C" int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b,
     if (splits > k_total / 8) splits = k_total / 8;
     if (splits < 1) splits = 1;
     const long long slice = static_cast<long long>(p.p_tiles) * 128 * p.q_tiles * p.q_tile * 4;
-    if (slice > ws_bytes) return CTRLORA_ERR_ARG;
-    if (splits * slice > ws_bytes) splits = static_cast<int>(ws_bytes / slice);
+    if (splits > 1) {
+        if (slice > ws_bytes) splits = 1;  // does not fit the workspace: single split, written directly
+        else if (splits * slice > ws_bytes) splits = static_cast<int>(ws_bytes / slice);
+    }
     p.kiters_per_split = (k_total + splits - 1) / splits;
     p.splits = (k_total + p.kiters_per_split - 1) / p.kiters_per_split;
+    p.direct = (p.splits == 1 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    p.out = out; p.ldo = ldo; p.alpha = alpha; p.beta = beta;
+    if (!p.direct && p.splits * slice > ws_bytes) return CTRLORA_ERR_ARG;
     p.stage_bytes = WG_A_BYTES + p.q_atoms * WG_BK * 128;
     p.idesc = umma_idesc_f16(128, p.q_tile, 0) | (1u << 15) | (1u << 16);  // A and B MN-major
     p.ws = ws;
@@ -226,8 +291,8 @@ extern "C" int ctrlora_wgrad_tn_f16(const void* a, long long lda, const void* b,
     if (launch_pdl(wgrad_tn_kernel, dim3(p.p_tiles * p.q_tiles, p.splits), dim3(WG_THREADS), (size_t)smem_bytes, stream, tmA,
                    tmB, p) != cudaSuccess)
         return CTRLORA_ERR_CUDA;
-    const long long total = static_cast<long long>(p_dim) * (q_dim / 4);
-    if (launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, stream,
+    if (p.direct) return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+    if (launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((p_dim + 31) / 32), (unsigned)((q_dim / 4 + 7) / 8)), dim3(256), (size_t)0, stream,
                    (const float*)ws, out, p_dim, q_dim, p.p_tiles * 128, p.q_tiles * p.q_tile, p.splits, ldo, alpha, beta) !=
         cudaSuccess)
         return CTRLORA_ERR_CUDA;

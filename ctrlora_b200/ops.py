@@ -775,3 +775,13 @@ def transpose_f16(src, batch, rows, cols):
     _count()
     check(_lib.load().ctrlora_transpose_f16(_dp(src), _dp(out), batch, rows, cols, _sp()), "transpose_f16")
     return out
+
+
+def conv_dgrad_weight(w16):
+    """fp16 conv kernel weight [Cout, taps, Cin] -> data-gradient weight [Cin, taps reversed, Cout]"""
+    _require_cuda(w16)
+    co, taps, ci = w16.shape
+    out = torch.empty((ci, taps, co), device=w16.device, dtype=torch.float16)
+    _count()
+    check(_lib.load().ctrlora_conv_dgrad_weight_f16(_dp(w16), _dp(out), co, taps, ci, _sp()), "conv_dgrad_weight")
+    return out

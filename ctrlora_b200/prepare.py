@@ -62,10 +62,10 @@ def _f32c(p):
     return t
 
 
-def linear_weight(weight):
-    """nn.Linear weight fp32 [N, K] -> fp16 [N, 1, K]"""
+def linear_weight(weight, out=None):
+    """nn.Linear weight fp32 [N, K] -> fp16 [N, 1, K] (written into `out`, a contiguous fp16 [N, 1, K] view, when given)"""
     n, k = weight.shape
-    return ops.cast_transpose(_f32c(weight), n * k, 1, 1).view(n, 1, k)
+    return ops.cast_transpose(_f32c(weight), n * k, 1, 1, out=out).view(n, 1, k)
 
 
 def conv_weight(weight, pad_in=None, pad_out=None):
@@ -84,7 +84,7 @@ def conv_weight(weight, pad_in=None, pad_out=None):
     return w
 
 
-def lora_folded_weight(weight, down, up, scale=1.0):
+def lora_folded_weight(weight, down, up, scale=1.0, out=None):
     """W' = W + scale * up @ down as fp16 [N, 1, K]  (cldm/lora.py:250 `_fuse_lora`, evaluated in fp32 accumulate).
 
     One tcgen05 GEMM: A = up [N, r], B = down^T [K, r], epilogue adds the fp32 master W.  Cost 2*N*K*r flop, once per
@@ -101,20 +101,21 @@ def lora_folded_weight(weight, down, up, scale=1.0):
         d2 = torch.zeros((k, 1, rp), device=up16.device, dtype=torch.float16)
         d2[:, :, :r] = down_t
         up16, down_t = u2, d2
-    out = torch.empty((n, k), device=weight.device, dtype=torch.float16)
+    out = torch.empty((n, k), device=weight.device, dtype=torch.float16) if out is None else out.view(n, k)
     ops.gemm(up16, down_t, residual=_f32c(weight), out_scale=scale, out=out)
     return out.view(n, 1, k)
 
 
-def effective_linear_weight(linear):
+def effective_linear_weight(linear, out=None):
     """fp16 [N,1,K] weight of an nn.Linear or a LoRACompatibleLinear (LoRA folded when a lora_layer is attached)."""
     lora = getattr(linear, "lora_layer", None)
     if lora is None:
-        return linear_weight(linear.weight)
+        return linear_weight(linear.weight, out=out)
     scale = 1.0
     if getattr(lora, "network_alpha", None) is not None:
         scale = lora.network_alpha / lora.rank  # cldm/lora.py:77-78
-    return lora_folded_weight(linear.weight, lora.down.weight, lora.up.weight, scale * getattr(linear, "_lora_scale", 1.0))
+    return lora_folded_weight(linear.weight, lora.down.weight, lora.up.weight, scale * getattr(linear, "_lora_scale", 1.0),
+                              out=out)
 
 
 def linear_params(linear):
@@ -153,4 +154,4 @@ def weight_T(w16):
 def conv_dgrad_weight(w16):
     """fp16 conv kernel weight [Cout, taps, Cin] -> data-gradient weight [Cin, taps (flipped), Cout]:
     dx = conv(dy, W_d) with the same 'same' padding."""
-    return w16.flip(1).permute(2, 1, 0).contiguous()
+    return ops.conv_dgrad_weight(w16.contiguous())

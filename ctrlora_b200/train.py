@@ -102,8 +102,21 @@ def lin_wT(lin):
 
 
 def cat_w(owner, key, lins):
+    """the stacked [sum N, 1, K] weight of projections that share their input (q|k|v, k|v): each effective weight is
+    produced straight into its row range"""
     params = [p for l in lins for p in prepare.linear_params(l)]
-    return _cache(owner).get((key, prepare.lora_key(*lins)), params, lambda: torch.cat([lin_w(l) for l in lins], 0).contiguous())
+
+    def build():
+        ns = [l.weight.shape[0] for l in lins]
+        k = lins[0].weight.shape[1]
+        out = torch.empty((sum(ns), 1, k), device=lins[0].weight.device, dtype=torch.float16)
+        o = 0
+        for l, n in zip(lins, ns):
+            prepare.effective_linear_weight(l, out=out[o:o + n])
+            o += n
+        return out
+
+    return _cache(owner).get((key, prepare.lora_key(*lins)), params, build)
 
 
 def cat_wT(owner, key, lins):

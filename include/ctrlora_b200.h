@@ -159,6 +159,11 @@ int ctrlora_cast_transpose_f32_to_f16(const float* src, void* dst, long long bat
 /* fp16 [batch, rows, cols] -> fp16 [batch, cols, rows] (transposed weight copies for the data-gradient GEMMs) */
 int ctrlora_transpose_f16(const void* src, void* dst, long long batch, int rows, int cols, void* stream);
 
+/* conv kernel weight fp16 [cout, taps, cin] -> data-gradient weight [cin, taps reversed, cout]: dx = conv(dy, W_d) with the
+ * same padding -- the adjoint of torch.nn.Conv2d (ldm/modules/diffusionmodules/util.py:224 conv_nd) that autograd applies;
+ * rebuilt every step in pretraining, where the conv weights train (cldm/cldm_ctrlora_pretrain.py:88-96). */
+int ctrlora_conv_dgrad_weight_f16(const void* src, void* dst, int cout, int taps, int cin, void* stream);
+
 /* DDIM update in one pass   cldm/ddim_hacked.py:190-192 (CFG, e_uncond may be NULL), :208-231 (pred_x0, x_prev).
  * fp32, round-to-nearest ops in the reference's order. stats (optional, [batch]) receives sum(x_prev^2) per image. */
 int ctrlora_ddim_update(const float* x, const float* e_cond, const float* e_uncond, const float* noise, float* x_prev,
