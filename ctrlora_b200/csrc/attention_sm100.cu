@@ -349,18 +349,22 @@ struct StreamSmem {
 };
 
 // P = exp2(s * sl2 + neg) for one 32-column chunk of one row; tmax tracks the raw row maximum over valid columns.
-template <bool MASK>
+// POLY = k > 0: the odd element of every k-th pair is evaluated on the FMA pipe (exp2_poly4): k = 1 half, k = 2 a quarter
+template <bool MASK, int POLY = ATT_POLY_EVERY>
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&raw)[32], float sl2, float neg, int c, int kv_valid,
                                               uint32_t (&packed)[16], float& tmax) {
     if (!MASK) {
+        float tm2 = -INFINITY;  // two independent maximum chains
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-            tmax = max3f(tmax, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            if (i & 2) tm2 = max3f(tm2, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+            else tmax = max3f(tmax, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
             const float p0 = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, neg));
             const float x1 = fmaf(__uint_as_float(raw[i + 1]), sl2, neg);
-            const float p1 = (ATT_POLY_EVERY > 0 && ((i >> 1) % ATT_POLY_EVERY) == ATT_POLY_EVERY - 1) ? exp2_poly3(x1) : fast_exp2(x1);
+            const float p1 = (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly4(x1) : fast_exp2(x1);
             packed[i >> 1] = pack_half2(p0, p1);
         }
+        tmax = fmaxf(tmax, tm2);
     } else {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -656,6 +660,276 @@ attention_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
 }
 
+// =====================================================================================================================
+// d_head 40 (SD1.5's 64x64 / 32x32 self-attention: d < 48 leaves the spare V^T row for the row sums): 64-key tiles,
+// S double-buffered in TMEM, eight softmax warps on split keys.
+// ncu on attention_stream_kernel<48> (profiles/prof_attn_stream_r1j) showed the four softmax warps waiting a quarter of
+// their time for S(j): the MMA warp can only start S(j+1) once softmax(j) has read the single S buffer.  Here
+//   * the key tile is 64 wide and S is DOUBLE-BUFFERED (S(j+1), S(j+2) are issued while softmax(j) runs; a row thread finds
+//     its logits waiting); K/V ride a four-stage ring;
+//   * warps w and w + 4 own the same 32 TMEM lanes (query rows) and run INDEPENDENT online-softmax streams over the lower /
+//     upper 32 keys of every tile -- own lazy reference, own accumulator (O_A, O_B), own row sum -- merged once at the end
+//     like split-KV decoding:  O = (2^(mA-m) O_A + 2^(mB-m) O_B) / (2^(mA-m) l_A + 2^(mB-m) l_B),  m = max(mA, mB).
+//     No per-tile exchange between the two warps of a row; four row-math warps per scheduler instead of two.
+//   TMEM: S0 64 | S1 64 | O_A 48 | O_B 48 | P 32 = 256 columns, two CTAs per SM.
+// Measured at 8 img x 8 heads x 4096 x 4096, d = 40 (CUDA events, tools/time_attn.py; MUFU bound 239 us):
+//   single S buffer, 128 keys (kernel above)                     434 us   XU pipe 57 %
+//   double-buffered S, 64 keys, 4 softmax warps                  383 us   XU pipe 65 % (profiles/prof_attn_stream64_r2w)
+//   + 8 warps, row maxima exchanged per tile (smem + bar.sync)   407 us   the exchange costs more than the warps hide
+//   + 8 warps, independent key halves (this kernel)              374 us
+//   exp2 on the FMA pipe for 1/6, 1/4, 1/2 of the elements       384 / 391 / 434 us (on the 4-warp form): not XU-throughput
+//   bound -- the warps stall on fixed-latency dependencies (ncu: stall_wait 31 %) -- so none of it is kept;
+//   prefetching S(j+1) from TMEM before handing over P(j)        411 us (4 warps), 788 us (8 warps: spills): dropped.
+struct Stream64 {
+    static constexpr int BKV = 64;
+    static constexpr int DPAD = 48;
+    static constexpr int NSTAGE = 4;
+    static constexpr int Q_BYTES = 128 * 128;
+    static constexpr int K_BYTES = BKV * 128;
+    static constexpr int V_BYTES = DPAD * 128;
+    static constexpr int STAGE_BYTES = K_BYTES + V_BYTES;
+    static constexpr int BAR_OFF = Q_BYTES + NSTAGE * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 256;
+};
+
+constexpr int ATT64S_THREADS = 320;  // warps 0-7 softmax (lane quarter = warp & 3, key half = warp >> 2), 8 TMA, 9 MMA
+
+__global__ void __launch_bounds__(ATT64S_THREADS, 2)
+attention_stream64s_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+    using L = Stream64;
+    constexpr int BKV = L::BKV, DPAD = L::DPAD, NS = L::NSTAGE;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;        // [NS]
+    uint64_t* kv_empty = bars + 1 + NS;  // [NS]
+    uint64_t* s_full = bars + 1 + 2 * NS;  // [2]
+    uint64_t* p_full = s_full + 2;
+    uint64_t* pv_full = s_full + 3;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_full + 4);
+    float* xm = reinterpret_cast<float*>(smem + L::BAR_OFF + 256);  // [128]: the upper half's final reference (in the 1 KiB tail)
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, img = blockIdx.z;
+    uint8_t* sQ = smem;
+    auto sK = [&](int stage) { return smem + L::Q_BYTES + stage * L::STAGE_BYTES; };
+    auto sV = [&](int stage) { return smem + L::Q_BYTES + stage * L::STAGE_BYTES + L::K_BYTES; };
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 9 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < NS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(p_full, 256);
+        mbar_init(pv_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tmem_s = tmem_base;                 // S0 [0, 64) | S1 [64, 128)
+    const uint32_t tmem_o = tmem_base + 2 * BKV;       // O_A [128, 176) | O_B [176, 224): column d is the row sum
+    const uint32_t tmem_p = tmem_o + 2 * DPAD;         // [224, 256): P as fp16 pairs, lower | upper key half
+    const int n_tiles = p.n_kv_tiles;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            mbar_expect_tx(q_full, 128 * 128);
+            tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, img);
+            const uint32_t tx = BKV * 128 + p.d16 * 128;
+            for (int j = 0; j < n_tiles; ++j) {
+                const int stage = j % NS;
+                if (j >= NS) mbar_wait(&kv_empty[stage], ((j / NS) - 1) & 1);
+                mbar_expect_tx(&kv_full[stage], tx);
+                tma_load_4d(sK(stage), &tmK, &kv_full[stage], 0, head, j * BKV, img);
+                tma_load_4d(sV(stage), &tmV, &kv_full[stage], j * BKV, 0, head, img);
+            }
+        }
+    } else if (warp == 9) {
+        // ---------------------------------------------------- MMA issuer (whole warp in the loop, one lane issues)
+        const int ksteps_s = (p.d + 15) / 16;
+        const uint32_t qa = smem_u32(sQ);
+        auto issue_s = [&](int j) {
+            const int stage = j % NS;
+            mbar_wait(&kv_full[stage], (j / NS) & 1);
+            if (lane < 8)
+                *reinterpret_cast<uint4*>(sV(stage) + p.d * 128 + lane * 16) =
+                    make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ka = smem_u32(sK(stage));
+                for (int ks = 0; ks < ksteps_s; ++ks)
+                    umma_f16(tmem_s + (j & 1) * BKV, umma_desc_kmajor_sw128(qa + ks * 32), umma_desc_kmajor_sw128(ka + ks * 32),
+                             p.idesc_s, ks != 0 ? 1u : 0u);
+                umma_commit(&s_full[j & 1]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        if (n_tiles > 1) issue_s(1);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int stage = j % NS;
+            mbar_wait(p_full, j & 1);  // P(j) is in TMEM and S(j) has been read out
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t va = smem_u32(sV(stage));
+                const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_f16_ts(tmem_o + h * DPAD, tmem_p + h * 16 + 8 * ks, umma_desc_kmajor_sw128(va + (2 * h + ks) * 32),
+                                    p.idesc_pv, (acc | ks) ? 1u : 0u);
+                umma_commit(pv_full);
+                umma_commit(&kv_empty[stage]);
+            }
+            __syncwarp();
+            if (j + 2 < n_tiles) issue_s(j + 2);
+        }
+    } else {
+        // ---------------------------------------------------- softmax: thread == (query row, key half)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const float sl2 = p.scale_log2e;
+        const uint32_t tp = tmem_p + lane_off + half * 16;
+        const uint32_t to = tmem_o + lane_off + half * DPAD;
+        float mr = -INFINITY;  // this half's lazy reference maximum, already multiplied by scale * log2(e)
+        for (int j = 0; j < n_tiles; ++j) {
+            const uint32_t ts = tmem_s + lane_off + (j & 1) * BKV + half * 32;
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const int kv_valid = max(0, min(32, p.Nk - j * BKV - half * 32));  // columns >= Nk are TMA zero fill
+            const bool full_tile = kv_valid == 32;  // warp-uniform
+            float tmax = -INFINITY;
+            uint32_t raw[32], packed[16];
+            tmem_ld_32x32(ts, raw);
+            tmem_ld_wait();
+            bool redo = (j == 0);
+            if (!redo) {
+                if (full_tile) softmax_chunk<false, 0>(raw, sl2, -mr, 0, kv_valid, packed, tmax);
+                else softmax_chunk<true, 0>(raw, sl2, -mr, 0, kv_valid, packed, tmax);
+                // P V(j-1) reads the P columns and accumulates into O: it must be done before P(j) is written
+                mbar_wait(pv_full, (j - 1) & 1);
+                tmem_st_32x16(tp, packed);
+                redo = __any_sync(0xffffffffu, tmax * sl2 > mr + ATT_TAU);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < kv_valid) tmax = fmaxf(tmax, __uint_as_float(raw[i]));
+            }
+            if (redo) {
+                const float tm = tmax * sl2;
+                const bool fix = tm > mr + ATT_TAU;            // first tile: mr = -inf -> every row
+                const float mr_new = fix ? tm : mr;
+                const float alpha = fix ? fast_exp2(mr - mr_new) : 1.0f;
+                mr = mr_new;
+                if (j > 0) {
+                    tc_fence_after();  // pv_full(j-1) was waited for above: O is quiescent
+#pragma unroll 1
+                    for (int c = 0; c < DPAD; c += 16) {
+                        uint32_t o[16];
+                        tmem_ld_32x16(to + c, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st_32x16(to + c, o);
+                    }
+                }
+                float dummy = 0.f;
+                softmax_chunk<true, 0>(raw, sl2, -mr, 0, kv_valid, packed, dummy);
+                tmem_st_32x16(tp, packed);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        // ---- merge the two key halves, normalise, store (the lower-half warps)
+        if (half == 1) xm[r] = mr;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (half == 0) {
+            const float mb = xm[r];
+            const float m = fmaxf(mr, mb);
+            const float wa = fast_exp2(mr - m), wb = fast_exp2(mb - m);
+            mbar_wait(pv_full, (n_tiles - 1) & 1);
+            tc_fence_after();
+            uint32_t la, lb;
+            tmem_ld_32x1(tmem_o + lane_off + p.d, la);
+            tmem_ld_32x1(tmem_o + lane_off + DPAD + p.d, lb);
+            tmem_ld_wait();
+            const float l_tot = wa * __uint_as_float(la) + wb * __uint_as_float(lb);
+            const float inv_l = 1.0f / l_tot;
+            const float ca = wa * inv_l, cb = wb * inv_l;
+            const bool row_ok = (q0 + r) < p.Nq;
+            if (p.lse && row_ok)
+                p.lse[(static_cast<long long>(img) * p.heads + head) * p.Nq + q0 + r] = m + log2f(l_tot);
+            __half* orow = p.out + (static_cast<long long>(img) * p.Nq + q0 + r) * p.ldo + head * p.d;
+#pragma unroll
+            for (int c = 0; c < DPAD; c += 16) {
+                if (c < p.d) {  // warp-uniform
+                    uint32_t oa[16], ob[16];
+                    tmem_ld_32x16(tmem_o + lane_off + c, oa);
+                    tmem_ld_32x16(tmem_o + lane_off + DPAD + c, ob);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if (c + g * 8 < p.d) {
+                                uint4 u;
+                                __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int i0 = g * 8 + 2 * e;
+                                    h[e] = __floats2half2_rn(
+                                        fmaf(ca, __uint_as_float(oa[i0]), cb * __uint_as_float(ob[i0])),
+                                        fmaf(ca, __uint_as_float(oa[i0 + 1]), cb * __uint_as_float(ob[i0 + 1])));
+                                }
+                                *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+static int launch_attn_stream64s(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                                 dim3 grid, cudaStream_t stream) {
+    using L = Stream64;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attention_stream64s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    if (launch_pdl(attention_stream64s_kernel, grid, dim3(ATT64S_THREADS), (size_t)L::TOTAL, stream, tq, tk, tv, p) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
 template <int DPAD>
 static int launch_attn_stream(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                               dim3 grid, cudaStream_t stream) {
@@ -709,7 +983,13 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
     p.out = reinterpret_cast<__half*>(out); p.ldo = ldo; p.lse = lse;
     const bool multi = nk > 256;
     if (multi && d > 80) return CTRLORA_ERR_UNSUPPORTED;  // d_head 160 with > 256 keys: not on the 512x512 path
-    const int bkv = multi ? 128 : (nk <= 128 ? 128 : 256);
+    static int stream64_env = -1;
+    if (stream64_env < 0) {
+        const char* e = getenv("CTRLORA_ATTN_STREAM64");
+        stream64_env = (e && e[0] == '0') ? 0 : 1;  // 0: the 128-key single-S-buffer kernel (kept for A/B measurements)
+    }
+    const bool s64 = multi && stream64_env && d < 48 && (d % 16) != 0;  // needs the spare V^T row and d16 <= 48
+    const int bkv = s64 ? 64 : multi ? 128 : (nk <= 128 ? 128 : 256);
     p.n_kv_tiles = (nk + bkv - 1) / bkv;
     p.idesc_s = umma_idesc_f16(128, bkv, 0);
     p.idesc_pv = umma_idesc_f16(128, p.d16, 0);
@@ -737,6 +1017,7 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
         if (rc) return rc;
     }
     dim3 grid((nq + 127) / 128, heads, batch);
+    if (s64) return launch_attn_stream64s(tq, tk, tv, p, grid, stream);
     if (multi) {
         static int stream_env = -1;
         if (stream_env < 0) {

@@ -504,4 +504,15 @@ __device__ __forceinline__ float exp2_poly3(float x) {
     p = fmaf(p, f, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// degree 4: max relative error 2.7e-6 in fp32 Horner form (ex2.approx itself: 2.4e-7; fp16 rounding of P: 4.9e-4)
+__device__ __forceinline__ float exp2_poly4(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(0.009570102f, f, 0.05591786f);
+    p = fmaf(p, f, 0.24024744f);
+    p = fmaf(p, f, 0.6931218f);
+    p = fmaf(p, f, 0.99999928f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 }  // namespace ctrl

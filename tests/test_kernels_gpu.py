@@ -101,6 +101,37 @@ def test_attention(B, H, Nq, Nk, d):
     _close(out, _attn_ref(q, k, v, B, H, Nq, Nk, d), 3e-3)
 
 
+@pytest.mark.parametrize("Nq,Nk,d,hot", [(256, 1000, 40, "upper"), (256, 1000, 40, "lower"), (130, 290, 24, "upper"),
+                                          (128, 4096, 40, "drift"), (64, 520, 8, "lower")])
+def test_attention_split_key_streams_and_lse(Nq, Nk, d, hot):
+    """The d < 48 streaming kernel runs two independent online-softmax streams per row (lower / upper 32 keys of every
+    64-key tile) and merges them at the end: put the dominant logits into one half only / let the maximum drift upwards
+    tile after tile, and check O and the saved log-sum-exp (base 2, scaled logits) against fp32 torch."""
+    from ctrlora_b200 import ops
+    torch.manual_seed(11)
+    B, H = 1, 4
+    q, k, v = _rand(B * Nq, H * d), _rand(B * Nk, H * d), _rand(B * Nk, H * d)
+    kk = k.view(B, Nk, H, d)
+    qq = q.view(B, Nq, H, d)
+    idx = torch.arange(Nk, device="cuda")
+    if hot in ("upper", "lower"):
+        sel = ((idx % 64) >= 32) if hot == "upper" else ((idx % 64) < 32)
+        kk[:, sel] += 1.5 * qq[:, :1].mean(1, keepdim=True).sign()  # logits of one key half stand well above the other
+        kk[:, sel] *= 2.0
+    else:
+        kk *= (1.0 + 3.0 * idx.float() / Nk).view(1, Nk, 1, 1).half()  # keys grow: the row maximum keeps moving
+    nk_pad = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, H, d, nk_pad, device="cuda", dtype=torch.float16)
+    vt[..., :Nk] = v.view(B, Nk, H, d).permute(0, 2, 3, 1)
+    lse = torch.empty(B, H, Nq, device="cuda", dtype=torch.float32)
+    out = ops.attention(q, k, vt, B, H, Nq, Nk, d, lse=lse)
+    _close(out, _attn_ref(q, k, v, B, H, Nq, Nk, d), 3e-3)
+    qf = q.float().view(B, Nq, H, d).permute(0, 2, 1, 3)
+    kf = k.float().view(B, Nk, H, d).permute(0, 2, 1, 3)
+    ref_lse = torch.logsumexp((qf @ kf.transpose(-1, -2)) * d ** -0.5, -1) * 1.4426950408889634
+    assert (lse - ref_lse).abs().max().item() < 2e-3 * max(1.0, ref_lse.abs().max().item())
+
+
 def test_attention_sharp_softmax():
     """Large logits (|s| ~ 30): the online-softmax rescaling must stay exact across KV tiles."""
     from ctrlora_b200 import ops

@@ -237,7 +237,9 @@ def test_non_square_sampling_loop_matches_per_step_oracle(mid):
             x_prev, _ = O.ddim_update(xs[i], O.cfg_combine(e_c, e_u, 7.5), tables, index)
             worst = max(worst, rel(xs[i + 1], x_prev))
     print(f"non-square sampling loop: worst per-step x_prev rel err {worst:.2e}")
-    assert worst < TOL["mid_eps"]  # x_prev is dominated by x: the (guidance-scaled) eps error enters with a small coefficient
+    # a 4-step schedule takes 250-timestep strides, so eps enters x_prev with an O(1) coefficient and the CFG combine
+    # (cldm/ddim_hacked.py:192) scales the two eps errors by 8.5 / 7.5: measured 3.2e-3 for a 1.5e-3 eps error
+    assert worst < TOL["mid_cfg_step"]
     assert rel(samples, xs[-1]) == 0.0
 
 

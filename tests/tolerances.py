@@ -24,6 +24,7 @@ TOL = {
     "tiny_grad_norm": 4.6e-3,    # worst of 246 (finetune) / 816 (pretrain) tensors over runs: 2.4e-3 .. 3.8e-3
     "tiny_grad_tensor": 7e-3,    # worst of 16 full tensors: 5.5e-3
     "mid_eps": 1.7e-3,           # 1.41e-3
+    "mid_cfg_step": 3.9e-3,      # 3.23e-3: x_prev of one CFG-7.5 DDIM step of a 4-step schedule, non-square latent
     "mid_ragged_eps": 2.05e-3,   # 1.46e-3 .. 1.70e-3 over six ragged / non-square shapes (8x8 at batch 5 is the worst)
     "sd15_eps": 1.9e-3,          # SD1.5 + ControlNet rank 128: 1.55e-3 (forward), 1.57e-3 (training forward, B = 2)
     "sd15_control": 1.8e-3,      # control[12] 1.50e-3, control[0][:8] 4.7e-4
