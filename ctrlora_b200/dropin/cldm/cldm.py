@@ -25,13 +25,19 @@ def _ctx16(context):
     return context_f16(context)
 
 
-class ControlledUnetModel(UNetModel):
+class ControlledForward:
+    """forward of ControlledUnetModel (reference cldm/cldm.py:22-45), shared with the IP-Adapter UNet of cldm/cldm_style.py"""
+
+    @staticmethod
+    def _context(context):
+        return _ctx16(context)
+
     def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
         """`control`: list of 13 residual tensors (or runtime.Scaled pairs), consumed with pop() like the reference."""
         hs = []
         with torch.no_grad():  # the SD encoder never receives gradients (reference :25-32)
             emb = self.embed(timesteps)
-            ctx = _ctx16(context)
+            ctx = self._context(context)
             h = x
             for module in self.input_blocks:
                 h = module(h, emb, ctx)
@@ -50,6 +56,10 @@ class ControlledUnetModel(UNetModel):
             spec = CatSpec(h, add1=add_mid if i == 0 else None, s1=s_mid, x2=skip, add2=add, s2=s)
             h = module(spec, emb, ctx)
         return self.final(h)
+
+
+class ControlledUnetModel(ControlledForward, UNetModel):
+    pass
 
 
 class ControlNet(nn.Module):

@@ -185,7 +185,9 @@ class DDIMSampler(object):
         of every sampling run and every 64th call (`full`); the trainer's fused AdamW bumps prepare.TRAIN_VERSION."""
         from ctrlora_b200 import prepare
         if self._fp_params is None:
-            self._fp_params = list(self.model.control_model.parameters()) + list(self.model.model.diffusion_model.parameters())
+            # parameters and buffers (the IP-Adapter's `ip_scale` is a buffer the style app rewrites per request)
+            self._fp_params = [t for m in (self.model.control_model, self.model.model.diffusion_model)
+                               for t in list(m.parameters()) + list(m.buffers())]
         ver = sum([p._version for p in self._fp_params])
         self._fp_calls += 1
         if full or self._fp_ptr is None or self._fp_calls % 64 == 0:

@@ -145,11 +145,7 @@ class CrossAttention(nn.Module):
             hit = self.__dict__.get("_kv_cache")
             if hit is not None and hit[0][1] == ctx2d.data_ptr() and hit[0][2] == self._kv_weight_token() and \
                     hit[1].shape[0] == batch * nk:
-                o = ops.attention(q, hit[1], hit[2], batch, h, nq, nk, d)
-                lin = self.to_out[0]
-                wo = self._prep.get(("o", prepare.lora_key(lin)), prepare.linear_params(lin),
-                                    lambda: prepare.effective_linear_weight(lin))
-                return ops.gemm(o, wo, bias=prepare.bias_f32(lin.bias), residual=residual)
+                return self._finish(ops.attention(q, hit[1], hit[2], batch, h, nq, nk, d), q, batch, nq, residual)
             k = torch.empty((batch * nk, inner), device=dev, dtype=torch.float16)
             # key padding columns (77 -> 80) are never written by the projection: they must hold finite values (their
             # probabilities are exactly 0, but 0 x NaN from recycled memory would poison the row) -> zero-initialised
@@ -157,11 +153,17 @@ class CrossAttention(nn.Module):
             w = self._cat_weight("kv", [self.to_k, self.to_v])
             ops.gemm(ctx2d, w, seg_outs=[k, vt], seg_width=inner, transposed=(0, 1, 0), rows_per_img=nk, head_dim=d,
                      tok_pad=nk_pad)
-        o = ops.attention(q, k, vt, batch, h, nq, nk, d)
+        return self._finish(ops.attention(q, k, vt, batch, h, nq, nk, d), q, batch, nq, residual)
+
+    def _out_weight(self):
         lin = self.to_out[0]
-        wo = self._prep.get(("o", prepare.lora_key(lin)), prepare.linear_params(lin),
-                            lambda: prepare.effective_linear_weight(lin))
-        return ops.gemm(o, wo, bias=prepare.bias_f32(lin.bias), residual=residual)
+        return self._prep.get(("o", prepare.lora_key(lin)), prepare.linear_params(lin),
+                              lambda: prepare.effective_linear_weight(lin))
+
+    def _finish(self, o, q, batch, nq, residual):
+        """to_out(attention output) (+ residual); `q` is handed on for variants that attend a second key set
+        (ldm/modules/attention_ip.py)."""
+        return ops.gemm(o, self._out_weight(), bias=prepare.bias_f32(self.to_out[0].bias), residual=residual)
 
     def forward(self, x, context=None, mask=None):
         if mask is not None:
@@ -176,6 +178,7 @@ MemoryEfficientCrossAttention = CrossAttention  # the xformers variant (referenc
 
 class BasicTransformerBlock(nn.Module):
     ATTENTION_MODES = {"softmax": CrossAttention, "softmax-xformers": MemoryEfficientCrossAttention}
+    attn2_cls = CrossAttention  # ldm/modules/attention_ip.py: IPCrossAttention
 
     def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True,
                  disable_self_attn=False):
@@ -184,8 +187,8 @@ class BasicTransformerBlock(nn.Module):
         self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
                                     context_dim=context_dim if disable_self_attn else None)
         self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
-        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
-                                    dropout=dropout)
+        self.attn2 = type(self).attn2_cls(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                                          dropout=dropout)
         self.norm1 = nn.LayerNorm(dim)
         self.norm2 = nn.LayerNorm(dim)
         self.norm3 = nn.LayerNorm(dim)
@@ -210,6 +213,8 @@ class BasicTransformerBlock(nn.Module):
 
 
 class SpatialTransformer(nn.Module):
+    block_cls = BasicTransformerBlock
+
     def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None, disable_self_attn=False,
                  use_linear=False, use_checkpoint=True):
         super().__init__()
@@ -223,8 +228,8 @@ class SpatialTransformer(nn.Module):
         else:
             self.proj_in = nn.Linear(in_channels, inner_dim)
         self.transformer_blocks = nn.ModuleList(
-            [BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
-                                   disable_self_attn=disable_self_attn, checkpoint=use_checkpoint) for d in range(depth)])
+            [type(self).block_cls(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
+                                  disable_self_attn=disable_self_attn, checkpoint=use_checkpoint) for d in range(depth)])
         if not use_linear:
             self.proj_out = zero_module(nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0))
         else:

@@ -208,6 +208,8 @@ def count_flops_attn(model, _x, y):
 class UNetModel(nn.Module):
     """The SD UNet (reference :412-786) restricted to the options the CtrLoRA configs use; unsupported options raise."""
 
+    transformer_cls = SpatialTransformer  # openaimodel_ip.UNetModel swaps in the IP-Adapter variant
+
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
                  use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
@@ -252,9 +254,9 @@ class UNetModel(nn.Module):
             nh, dh = heads_of(ch)
             if legacy:
                 dh = ch // nh
-            return SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim,
-                                      disable_self_attn=disable_sa, use_linear=use_linear_in_transformer,
-                                      use_checkpoint=use_checkpoint)
+            return type(self).transformer_cls(ch, nh, dh, depth=transformer_depth, context_dim=context_dim,
+                                              disable_self_attn=disable_sa, use_linear=use_linear_in_transformer,
+                                              use_checkpoint=use_checkpoint)
 
         def resblock(cin, cout):
             return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, dims=dims, use_checkpoint=use_checkpoint,

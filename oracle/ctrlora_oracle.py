@@ -65,7 +65,13 @@ def res_block(sd, p, x, emb):
 
 
 def cross_attention(sd, p, x, context, heads):
-    """CrossAttention.forward, ldm/modules/attention.py:163-194: fp32 logits, scale d_head^-0.5, softmax over keys."""
+    """CrossAttention.forward, ldm/modules/attention.py:163-194: fp32 logits, scale d_head^-0.5, softmax over keys.
+    A context given as the pair [text, ip] is the IP-Adapter variant, ldm/modules/attention_ip.py:218-289: a second
+    softmax over the image tokens through to_k_ip / to_v_ip, added with the module's `ip_scale` buffer before to_out
+    (self-attention layers and modules without to_k_ip use the text entry only, like CrossAttention given a tensor)."""
+    ip = None
+    if isinstance(context, (list, tuple)):
+        context, ip = context
     ctx = x if context is None else context
     q, k, v = linear(sd, p + ".to_q", x), linear(sd, p + ".to_k", ctx), linear(sd, p + ".to_v", ctx)
     b, n, c = q.shape
@@ -75,6 +81,11 @@ def cross_attention(sd, p, x, context, heads):
     sim = torch.einsum("bhid,bhjd->bhij", q.float(), k.float()) * (d ** -0.5)
     out = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
     out = out.permute(0, 2, 1, 3).reshape(b, n, c)
+    if ip is not None and (p + ".to_k_ip.weight") in sd:
+        k_ip, v_ip = split(linear(sd, p + ".to_k_ip", ip.float())), split(linear(sd, p + ".to_v_ip", ip.float()))
+        sim_ip = torch.einsum("bhid,bhjd->bhij", q.float(), k_ip.float()) * (d ** -0.5)
+        out_ip = torch.einsum("bhij,bhjd->bhid", sim_ip.softmax(dim=-1), v_ip).permute(0, 2, 1, 3).reshape(b, n, c)
+        out = out + sd[p + ".ip_scale"] * out_ip
     return linear(sd, p + ".to_out.0", out)
 
 
@@ -88,7 +99,7 @@ def feed_forward(sd, p, x):
 def transformer_block(sd, p, x, context, heads):
     """BasicTransformerBlock._forward, ldm/modules/attention.py:271-275."""
     x = cross_attention(sd, p + ".attn1", layer_norm(sd, p + ".norm1", x), None, heads) + x
-    x = cross_attention(sd, p + ".attn2", layer_norm(sd, p + ".norm2", x), context, heads) + x
+    x = cross_attention(sd, p + ".attn2", layer_norm(sd, p + ".norm2", x), context, heads) + x  # context may be [text, ip]
     x = feed_forward(sd, p + ".ff", layer_norm(sd, p + ".norm3", x)) + x
     return x
 

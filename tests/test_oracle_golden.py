@@ -154,3 +154,21 @@ def test_lora_linear_semantics(g):
     close(w_f, L["w_fused_0.7"], 1e-6)
     close(torch.nn.functional.linear(x, w_f, lsd["bias"]), L["y_fused_0.7"], 1e-5)
     close(lsd["weight"], L["w_unfused"], 1e-6)  # fuse -> unfuse round trip (lora.py:279)
+
+
+def test_ip_adapter_branch_vs_reference_golden():
+    """IPCrossAttention (ldm/modules/attention_ip.py:196-289) in the oracle against the reference's style UNet without
+    hint (`eps_no_hint`: control None, every attn2 receives [text, ip]); ip_scale 1 on the decoder layers, 0 elsewhere."""
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "tiny_style_golden.pt"), weights_only=False)
+    B, H, seed = g["B"], g["H"], g["seed"]
+    unet = synth.synth_state_dict(g["unet_shapes"], seed, "model.diffusion_model.")
+    assert sorted(k for k in unet if k.endswith("ip_scale")) == sorted(g["ip_scale_keys"]) and len(g["ip_scale_keys"]) == 16
+    for k, v in g["ip_scales_some"].items():
+        unet[k] = torch.tensor(v)
+    x, ctx = synth.synth_input("x", (B, 4, H, H), seed), synth.synth_input("ctx", (B, 77, 64), seed)
+    ip = synth.synth_input("ip", (B, 4, 64), seed)
+    with torch.no_grad():
+        eps = O.unet_forward(unet, x, g["t"], [ctx, ip], HEADS, MC, None)
+        close(eps, g["eps_no_hint"])
+        plain = O.unet_forward(unet, x, g["t"], ctx, HEADS, MC, None)
+    assert ((plain - g["eps_no_hint"]).norm() / g["eps_no_hint"].norm()).item() > 1e-3  # the image prompt matters

@@ -481,6 +481,57 @@ def schedule():
     print("wrote", out)
 
 
+def style(seed=0):
+    """IP-Adapter / style variant (tiny config): cldm.cldm_ctrlora_style_inference.ControlInferenceLDM with the UNet of
+    cldm.cldm_style (IPCrossAttention in every attn2, ldm/modules/attention_ip.py:196-289).  apply_model with image-prompt
+    tokens at two ip_scale settings (all layers / only some layers, as app/gradio_ctrlora_style_transfer.py:131-171 sets
+    them), without image prompt, and without hint (guess mode: control None)."""
+    txt = open(os.path.join(GOLD, "tiny_finetune.yaml")).read()
+    txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlFinetuneLDM", "cldm.cldm_ctrlora_style_inference.ControlInferenceLDM")
+    txt = txt.replace("cldm.cldm_ctrlora_finetune.ControlNetFinetune", "cldm.cldm_ctrlora_style_inference.ControlNetInference")
+    txt = txt.replace("cldm.cldm.ControlledUnetModel", "cldm.cldm_style.ControlledUnetModel")
+    txt = txt.replace("        ft_with_lora: True\n        lora_rank: 8\n        norm_trainable: True\n",
+                      "        lora_rank: 8\n        lora_num: 1\n")
+    assert "ft_with_lora" not in txt and "cldm_style" in txt
+    yaml_path = os.path.join(GOLD, "tiny_style.yaml")
+    with open(yaml_path, "w") as f:
+        f.write(txt)
+    B, H = 2, 16
+    x = synth.synth_input("x", (B, 4, H, H), seed)
+    hint = synth.synth_input("hint", (B, 4, H, H), seed)
+    ctx = synth.synth_input("ctx", (B, 77, 64), seed)
+    ip = synth.synth_input("ip", (B, 4, 64), seed)
+    t = torch.tensor([981, 21], dtype=torch.long)
+    model = build_reference(yaml_path, seed)
+    model.encode_first_stage = lambda h: h
+    model.get_first_stage_encoding = lambda h: h
+    unet = model.model.diffusion_model
+    g = {"seed": seed, "B": B, "H": H, "t": t, "control_shapes": shapes_of(model.control_model), "unet_shapes": shapes_of(unet),
+         "unet_key_order": list(unet.state_dict().keys())}
+    scale_keys = [k for k in unet.state_dict() if k.endswith("ip_scale")]
+    g["ip_scale_keys"] = scale_keys
+
+    def set_scales(values):
+        unet.load_state_dict({k: torch.tensor(v) for k, v in values.items()}, strict=False)
+
+    cond = [{"c_crossattn": [ctx], "c_concat": [hint], "c_ip": [ip]}]
+    with torch.no_grad():
+        # synth weights give every ip_scale buffer a random value: first the state as loaded
+        g["ip_scales_loaded"] = {k: float(unet.state_dict()[k]) for k in scale_keys}
+        g["eps_loaded"] = model.apply_model(x, t, cond)
+        set_scales({k: 0.8 for k in scale_keys})
+        g["eps_all_0.8"] = model.apply_model(x, t, cond)
+        some = {k: (1.0 if "output_blocks" in k else 0.0) for k in scale_keys}
+        set_scales(some)
+        g["ip_scales_some"] = some
+        g["eps_some"] = model.apply_model(x, t, cond)
+        g["eps_no_ip"] = model.apply_model(x, t, [{"c_crossattn": [ctx], "c_concat": [hint]}])
+        g["eps_no_hint"] = model.apply_model(x, t, [{"c_crossattn": [ctx], "c_concat": [None], "c_ip": [ip]}])
+    out = os.path.join(GOLD, "tiny_style_golden.pt")
+    torch.save(g, out)
+    print("wrote", out, os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
@@ -490,6 +541,7 @@ if __name__ == "__main__":
     ap.add_argument("--ranks", action="store_true")
     ap.add_argument("--vae", action="store_true")
     ap.add_argument("--vae-full", action="store_true")
+    ap.add_argument("--style", action="store_true")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if a.full:
@@ -506,5 +558,7 @@ if __name__ == "__main__":
         vae()
     elif a.vae_full:
         vae(full=True)
+    elif a.style:
+        style()
     else:
         tiny()
