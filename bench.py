@@ -450,6 +450,27 @@ def run_pretrain(args, rank, local_rank, world, device):
                          "note": "algorithmically necessary 2.33 TFLOP/image (finetune step + dense ControlNet weight gradients)"}}
 
 
+def attention_roofline(device, batch=2 * BATCH, heads=8, n=LATENT * LATENT, d=40, reps=20):
+    """CUDA-event time of the step's dominant attention launch (64x64 self-attention of a CFG batch) on its own."""
+    from ctrlora_b200 import ops
+    g = torch.Generator(device=device).manual_seed(7)
+    mk = lambda *s: (torch.randn(*s, device=device, generator=g) * 0.5).half()
+    q, k, v = mk(batch * n, heads * d), mk(batch * n, heads * d), mk(batch * n, heads * d)
+    vt = v.view(batch, n, heads, d).permute(0, 2, 3, 1).contiguous()
+    out = torch.empty_like(q)
+    for _ in range(3):
+        ops.attention(q, k, vt, batch, heads, n, n, d, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ops.attention(q, k, vt, batch, heads, n, n, d, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    exps = float(batch) * heads * n * n
+    return {"us": e0.elapsed_time(e1) * 1e3 / reps, "exps": exps, "flops": 4.0 * exps * d}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -599,6 +620,7 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 implicit GEMM): the step's GEMM launches are recorded on an
     # un-graphed step, then replayed back to back from one CUDA graph between two CUDA events (ops.replay_gemms)
     gemm_stats = ops.replay_gemms(one_step_in_run, sampler)
+    attn_stats = attention_roofline(device)
 
     t = torch.tensor([ms_dev, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
@@ -631,6 +653,16 @@ def main():
                              "traffic_source": ncu_gemm_traffic()[1],
                              "launches": gemm_stats["launches"], "gflop_per_step": gemm_stats["flops"] / 1e9,
                              "share_of_step": gemm_stats["ms"] / (ms_dev / args.steps)}}
+        # second kernel of the step (19 % of it): the d_head-40 self-attention of the 64x64 level, bound by exp2 throughput
+        sm_mhz = (clk or {}).get("sm_mhz") or 1900.0
+        peak_exp = 16.0 * torch.cuda.get_device_properties(device).multi_processor_count * sm_mhz * 1e6 / 1e12
+        a_ach = attn_stats["exps"] / (attn_stats["us"] * 1e-6) / 1e12
+        line["roofline_attention"] = {
+            "kernel": "attention_stream64s_kernel (7 launches per step: 8 img x 8 heads x 4096 x 4096, d = 40)",
+            "bound": "mufu (16 ex2 per clock per SM at the sampled SM clock)", "achieved": a_ach, "peak": peak_exp,
+            "unit": "Texp/s", "frac": a_ach / peak_exp, "us_per_launch": attn_stats["us"],
+            "tensor_tflops": attn_stats["flops"] / (attn_stats["us"] * 1e-6) / 1e12,
+            "share_of_step": 7 * attn_stats["us"] * 1e-3 / (ms_dev / args.steps)}
         if train_result is not None:
             line["train"] = train_result
             # BASELINE.json's second headline metric, lifted to the top level so that the scaling record keeps it

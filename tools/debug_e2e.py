@@ -36,3 +36,16 @@ for i, t in enumerate(T):
     print(i, " ".join(f"{v * 1e3:7.3f}" for v in t), f"total {sum(t) * 1e3:7.3f} ms")
 import statistics
 print("median h2d/enqueue/wait/hostcopy ms:", [round(statistics.median(t[j] for t in T[8:]) * 1e3, 3) for j in range(4)])
+if os.environ.get("E2E_PROFILE"):
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for i in range(40):
+        d = {k: host[k].to(device, non_blocking=True) for k in host}
+        c = {"c_crossattn": [d["ctx"]], "c_concat": [d["hint"]]}; u = {"c_crossattn": [d["uc"]], "c_concat": [d["hint"]]}
+        xp, _ = step(i, d["x"], c, u)
+        out_host.copy_(xp, non_blocking=True); stats_host.copy_(sampler.last_stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host["x"].copy_(out_host)
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
