@@ -930,6 +930,279 @@ static int launch_attn_stream64s(const CUtensorMap& tq, const CUtensorMap& tk, c
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
 }
 
+// =====================================================================================================================
+// Cross-attention to a short context (Nk <= 128: the 77 text tokens), d_head <= 80: the 64x64 and 32x32 levels.
+// attention_kernel<.., false> gives every (128 queries, head, image) its own CTA, and each CTA is one short serial chain
+// (TMA -> S -> two TMEM passes over 128 columns -> P -> P V over 128 keys -> epilogue): 46 us for 3 GF at the 64x64 level.
+// This kernel is PERSISTENT over the query tiles of one (head, image): K and V^T are loaded once, Q tiles ride a two-stage
+// TMA ring, S and O are double-buffered in TMEM, and the softmax warps run the epilogue of tile i-1 AFTER the softmax of
+// tile i, so the S / P V products and their latencies hide behind row math.  (Four dedicated epilogue warps were tried
+// instead: 36 us against 29 us at the 64x64 level -- dropped.)  Measured (tools/time_attn_cross.py, batch 8): 64x64 level
+// 43.8 -> 29.0 us, 32x32 level 16.7 -> 12.7 us; batch 16: 77 -> 52 us.  Only ceil(Nk / 32) 32-column chunks of S are
+// read (once: the tile's logits stay in registers between the max and the exp pass) and P V runs ceil(Nk / 16) k-steps.
+template <int DPAD>
+struct CrossSmem {
+    static constexpr int NKC = (DPAD + 63) / 64;
+    static constexpr int K_BYTES = NKC * 128 * 128;
+    static constexpr int V_CHUNK = DPAD * 128;
+    static constexpr int V_BYTES = 2 * V_CHUNK;
+    static constexpr int Q_STAGE = NKC * 128 * 128;
+    static constexpr int P_BUF = 2 * 128 * 128;
+    static constexpr int K_OFF = 0;
+    static constexpr int V_OFF = K_BYTES;
+    static constexpr int Q_OFF = V_OFF + V_BYTES + ((1024 - (V_BYTES & 1023)) & 1023);  // 1 KiB aligned (SWIZZLE_128B)
+    static constexpr int P_OFF = Q_OFF + 2 * Q_STAGE;
+    static constexpr int ONES_OFF = P_OFF + 2 * P_BUF;
+    static constexpr int BAR_OFF = ONES_OFF + 2048;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int O_STRIDE = DPAD + 16;  // O | l (row sums from P x ones)
+    static constexpr int TMEM_COLS = 512;       // S0 128 | S1 128 | (O | l) x 2
+};
+
+template <int DPAD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p, int splits) {
+    using L = CrossSmem<DPAD>;
+    pdl_launch_dependents();
+    // this CTA's query tiles of one (head, image)
+    const int pair = blockIdx.x / splits, part = blockIdx.x % splits;
+    const int head = pair % p.heads, img = pair / p.heads;
+    const int n_q_tiles = (p.Nq + 127) / 128;
+    const int t0 = static_cast<int>(static_cast<long long>(n_q_tiles) * part / splits);
+    const int t1 = static_cast<int>(static_cast<long long>(n_q_tiles) * (part + 1) / splits);
+    const int n = t1 - t0;
+    if (n <= 0) return;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* kv_full = bars;
+    uint64_t* q_full = bars + 1;    // [2]
+    uint64_t* q_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;    // [2]
+    uint64_t* p_full = bars + 7;    // [2]
+    uint64_t* pv_full = bars + 9;   // [2]
+    uint64_t* o_free = bars + 11;   // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+    uint8_t* sK = smem + L::K_OFF;
+    uint8_t* sV = smem + L::V_OFF;
+    uint8_t* sOnes = smem + L::ONES_OFF;
+    auto sQ = [&](int st) { return smem + L::Q_OFF + st * L::Q_STAGE; };
+    auto sP = [&](int b) { return smem + L::P_OFF + b * L::P_BUF; };
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 5 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&pv_full[i], 1);
+            mbar_init(&o_free[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, L::TMEM_COLS);
+    if (threadIdx.x < 128)  // 128 x 16 B = 2 KiB of 1.0h; all elements equal, so the swizzle is irrelevant
+        reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();
+    const uint32_t tmem_s = tmem_base;  // S buffer b at + 128 b
+    auto tmem_o = [&](int b) { return tmem_base + 256 + b * L::O_STRIDE; };
+    const int ksteps_pv = (p.Nk + 15) / 16;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer: K, V^T once, then the Q tiles
+            mbar_expect_tx(kv_full, p.nkc * 128 * 128 + 2 * p.d16 * 128);
+            for (int kc = 0; kc < p.nkc; ++kc) tma_load_4d(sK + kc * 128 * 128, &tmK, kv_full, kc * 64, head, 0, img);
+            for (int c = 0; c < 2; ++c) tma_load_4d(sV + c * L::V_CHUNK, &tmV, kv_full, c * 64, 0, head, img);
+            for (int i = 0; i < n; ++i) {
+                const int st = i & 1;
+                if (i >= 2) mbar_wait(&q_empty[st], ((i >> 1) - 1) & 1);
+                mbar_expect_tx(&q_full[st], p.nkc * 128 * 128);
+                for (int kc = 0; kc < p.nkc; ++kc)
+                    tma_load_4d(sQ(st) + kc * 128 * 128, &tmQ, &q_full[st], kc * 64, head, (t0 + i) * 128, img);
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------------------------------------------- MMA issuer (whole warp in the loop, one lane issues)
+        const int ksteps_s = (p.d + 15) / 16;
+        const uint32_t ka = smem_u32(sK), va = smem_u32(sV), oa = smem_u32(sOnes);
+        auto issue_s = [&](int i) {
+            const int st = i & 1;
+            mbar_wait(&q_full[st], (i >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t qa = smem_u32(sQ(st));
+                for (int ks = 0; ks < ksteps_s; ++ks) {
+                    const uint32_t off = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    umma_f16(tmem_s + st * 128, umma_desc_kmajor_sw128(qa + off), umma_desc_kmajor_sw128(ka + off), p.idesc_s,
+                             ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[st]);
+                umma_commit(&q_empty[st]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(kv_full, 0);
+        issue_s(0);
+        for (int i = 0; i < n; ++i) {
+            const int b = i & 1;
+            if (i + 1 < n) issue_s(i + 1);  // its S buffer was read out before p_full(i-1), waited for last iteration
+            mbar_wait(&p_full[b], (i >> 1) & 1);
+            if (i >= 2) mbar_wait(&o_free[b], ((i >> 1) - 1) & 1);  // the epilogue of tile i-2 has read this O buffer
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t pa = smem_u32(sP(b));
+                for (int ks = 0; ks < ksteps_pv; ++ks) {
+                    const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    const uint32_t off_v = (ks >> 2) * L::V_CHUNK + (ks & 3) * 32;
+                    umma_f16(tmem_o(b), umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(va + off_v), p.idesc_pv,
+                             ks != 0 ? 1u : 0u);
+                }
+                for (int ks = 0; ks < ksteps_pv; ++ks) {
+                    const uint32_t off_p = (ks >> 2) * 128 * 128 + (ks & 3) * 32;
+                    umma_f16(tmem_o(b) + DPAD, umma_desc_kmajor_sw128(pa + off_p), umma_desc_kmajor_sw128(oa), p.idesc_l,
+                             ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&pv_full[b]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------- softmax + epilogue: thread == query row
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const float sl2 = p.scale_log2e;
+        const int nch = (p.Nk + 31) / 32;  // 32-column chunks that hold keys (warp-uniform)
+        float m_tile[2] = {0.f, 0.f};
+        auto epilogue = [&](int j) {
+            const int b = j & 1;
+            mbar_wait(&pv_full[b], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t lraw;
+            tmem_ld_32x1(tmem_o(b) + DPAD + lane_off, lraw);
+            tmem_ld_wait();
+            const float l_tot = __uint_as_float(lraw);
+            const float inv_l = 1.0f / l_tot;
+            const int row = (t0 + j) * 128 + r;
+            const bool row_ok = row < p.Nq;
+            if (p.lse && row_ok) p.lse[(static_cast<long long>(img) * p.heads + head) * p.Nq + row] = m_tile[b] * sl2 + log2f(l_tot);
+            __half* orow = p.out + (static_cast<long long>(img) * p.Nq + row) * p.ldo + head * p.d;
+#pragma unroll
+            for (int c = 0; c < DPAD; c += 16) {
+                if (c < p.d) {  // warp-uniform
+                    uint32_t raw[16];
+                    tmem_ld_32x16(tmem_o(b) + lane_off + c, raw);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if (c + g * 8 < p.d) {
+                                uint4 u;
+                                __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    h[e] = __floats2half2_rn(__uint_as_float(raw[g * 8 + 2 * e]) * inv_l,
+                                                             __uint_as_float(raw[g * 8 + 2 * e + 1]) * inv_l);
+                                *reinterpret_cast<uint4*>(orow + c + g * 8) = u;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&o_free[b]);
+        };
+        for (int i = 0; i < n; ++i) {
+            const int b = i & 1;
+            mbar_wait(&s_full[b], (i >> 1) & 1);
+            tc_fence_after();
+            // the tile's logits, read once
+            uint32_t s[4][32];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nch) tmem_ld_32x32(tmem_s + b * 128 + lane_off + 32 * k, s[k]);
+            tmem_ld_wait();
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < nch) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (32 * k + c < p.Nk) m = fmaxf(m, __uint_as_float(s[k][c]));
+                }
+            }
+            m_tile[b] = m;
+            const float neg = -m * sl2;
+            const uint32_t pbase = smem_u32(sP(b));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < nch) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        const float p0 = (32 * k + c < p.Nk) ? fast_exp2(fmaf(__uint_as_float(s[k][c]), sl2, neg)) : 0.f;
+                        const float p1 = (32 * k + c + 1 < p.Nk) ? fast_exp2(fmaf(__uint_as_float(s[k][c + 1]), sl2, neg)) : 0.f;
+                        packed[c >> 1] = pack_half2(p0, p1);
+                    }
+                    store_p_chunk(pbase, r, 32 * k, packed);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[b]);
+            if (i >= 1) epilogue(i - 1);  // P V(i-1) has long finished: its latency hid behind this tile's row math
+        }
+        epilogue(n - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+template <int DPAD>
+static int launch_attn_cross(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                             int batch, cudaStream_t stream) {
+    using L = CrossSmem<DPAD>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(attention_cross_kernel<DPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+            cudaSuccess)
+            return CTRLORA_ERR_CUDA;
+        attr = true;
+    }
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int pairs = p.heads * batch, n_q_tiles = (p.Nq + 127) / 128;
+    int splits = sms / pairs;  // (head, image) pairs first; split their query tiles only while SMs are left over
+    if (splits < 1) splits = 1;
+    if (splits > n_q_tiles) splits = n_q_tiles;
+    if (launch_pdl(attention_cross_kernel<DPAD>, dim3(pairs * splits), dim3(ATT_THREADS), (size_t)L::TOTAL, stream, tq, tk, tv, p,
+                   splits) != cudaSuccess)
+        return CTRLORA_ERR_CUDA;
+    return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
 template <int DPAD>
 static int launch_attn_stream(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                               dim3 grid, cudaStream_t stream) {
@@ -1030,6 +1303,19 @@ extern "C" int ctrlora_attention_f16(const void* q, long long ldq, const void* k
         }
         if (d <= 48) return launch_attn<48, 128, true>(tq, tk, tv, p, grid, stream);
         return launch_attn<80, 128, true>(tq, tk, tv, p, grid, stream);
+    }
+    if (bkv == 128 && d <= 80) {
+        static int cross_env = -1;
+        if (cross_env < 0) {
+            const char* e = getenv("CTRLORA_ATTN_CROSS");
+            cross_env = (e && e[0] == '0') ? 0 : 1;  // 0: one CTA per query tile (kept for A/B measurements)
+        }
+        if (cross_env) {
+            AttnParams pc = p;
+            pc.idesc_s = umma_idesc_f16(128, (nk + 15) / 16 * 16, 0);  // only the key columns that exist
+            if (d <= 48) return launch_attn_cross<48>(tq, tk, tv, pc, batch, stream);
+            return launch_attn_cross<80>(tq, tk, tv, pc, batch, stream);
+        }
     }
     if (bkv == 128) {
         if (d <= 48) return launch_attn<48, 128, false>(tq, tk, tv, p, grid, stream);

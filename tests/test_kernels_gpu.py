@@ -132,6 +132,27 @@ def test_attention_split_key_streams_and_lse(Nq, Nk, d, hot):
     assert (lse - ref_lse).abs().max().item() < 2e-3 * max(1.0, ref_lse.abs().max().item())
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(1, 2, 130, 128, 64), (2, 3, 900, 100, 40), (1, 1, 128, 33, 8), (5, 8, 256, 77, 40),
+                                         (1, 8, 4096, 77, 40), (3, 8, 1000, 77, 80), (20, 8, 64, 77, 80)])
+def test_attention_short_context_persistent_kernel_and_lse(B, H, Nq, Nk, d):
+    """Nk <= 128, d <= 80 runs the persistent cross-attention kernel (K / V^T resident, query tiles streamed, S and O
+    double-buffered): ragged last query tile, 1 .. 32 tiles per CTA, full 128-key tile, more (head, image) pairs than SMs;
+    output and saved log-sum-exp against fp32 torch."""
+    from ctrlora_b200 import ops
+    torch.manual_seed(B * Nq + Nk)
+    q, k, v = _rand(B * Nq, H * d), _rand(B * Nk, H * d), _rand(B * Nk, H * d)
+    nk_pad = (Nk + 7) // 8 * 8
+    vt = torch.zeros(B, H, d, nk_pad, device="cuda", dtype=torch.float16)
+    vt[..., :Nk] = v.view(B, Nk, H, d).permute(0, 2, 3, 1)
+    lse = torch.empty(B, H, Nq, device="cuda", dtype=torch.float32)
+    out = ops.attention(q, k, vt, B, H, Nq, Nk, d, lse=lse)
+    _close(out, _attn_ref(q, k, v, B, H, Nq, Nk, d), 3e-3)
+    qf = q.float().view(B, Nq, H, d).permute(0, 2, 1, 3)
+    kf = k.float().view(B, Nk, H, d).permute(0, 2, 1, 3)
+    ref_lse = torch.logsumexp((qf @ kf.transpose(-1, -2)) * d ** -0.5, -1) * 1.4426950408889634
+    assert (lse - ref_lse).abs().max().item() < 2e-3 * max(1.0, ref_lse.abs().max().item())
+
+
 def test_attention_sharp_softmax():
     """Large logits (|s| ~ 30): the online-softmax rescaling must stay exact across KV tiles."""
     from ctrlora_b200 import ops
