@@ -82,6 +82,7 @@ _ARGTYPES = {
     "ctrlora_cast_transpose_f32_to_f16": [_P, _P, _L, _I, _I, _P],
     "ctrlora_transpose_f16": [_P, _P, _L, _I, _I, _P],
     "ctrlora_conv_dgrad_weight_f16": [_P, _P, _I, _I, _I, _P],
+    "ctrlora_set_sm_limit": [_I],
     "ctrlora_ddim_update": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P],
     "ctrlora_wgrad_tn_f16": [_P, _L, _P, _L, _I, _I, _I, _P, _L, _F, _F, _P, _L, _P],
     "ctrlora_groupnorm_bwd_f16": [_P, _P, _P, _P, _L, _F, _P, _L, _F, _P, _L, _P, _P, _P],
@@ -145,6 +146,7 @@ EXPORTS = [
     "ctrlora_cast_transpose_f32_to_f16",
     "ctrlora_transpose_f16",
     "ctrlora_conv_dgrad_weight_f16",
+    "ctrlora_set_sm_limit",
     "ctrlora_ddim_update",
     "ctrlora_wgrad_tn_f16",
     "ctrlora_attention_bwd_f16",

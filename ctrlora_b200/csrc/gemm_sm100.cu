@@ -649,6 +649,7 @@ static int pow2_floor(int x) {
 }
 
 static int g_num_sms = 0;
+static int g_sm_limit = 0;  // > 0: persistent grids leave SMs free for a concurrently running collective (ctrlora_set_sm_limit)
 static bool g_attr_set = false;
 
 }  // namespace ctrl
@@ -894,14 +895,15 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     cudaError_t lrc;
     if (pair) {
         const int units = ((m_tiles + 1) / 2) * p.n_tiles;           // one unit = one 256-row tile for one CTA pair
-        int clusters = g_num_sms / 2;
+        int clusters = (g_sm_limit > 0 && g_sm_limit < g_num_sms ? g_sm_limit : g_num_sms) / 2;
         if (units < clusters) clusters = units;
         const dim3 grid2(2 * clusters), block(GEMM_THREADS);
         lrc = p.geglu ? launch_cluster(gemm_tcgen05_kernel<true, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, em, p)
                       : launch_cluster(gemm_tcgen05_kernel<false, true>, grid2, block, (size_t)GEMM_SMEM_BYTES, stream, 2u, tmA, tmB, tmA2, tmB2, em, p);
     } else {
         const int total = m_tiles * p.n_tiles * p.splits;
-        const int grid = total < g_num_sms ? total : g_num_sms;
+        const int sms_avail = g_sm_limit > 0 && g_sm_limit < g_num_sms ? g_sm_limit : g_num_sms;
+        const int grid = total < sms_avail ? total : sms_avail;
         lrc = p.geglu ? launch_pdl(gemm_tcgen05_kernel<true, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
                                    stream, tmA, tmB, tmA2, tmB2, em, p)
                       : launch_pdl(gemm_tcgen05_kernel<false, false>, dim3(grid), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES,
@@ -909,4 +911,13 @@ extern "C" int ctrlora_gemm_f16(const ctrlora_gemm_args* a, void* stream_) {
     }
     if (lrc != cudaSuccess) return CTRLORA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? CTRLORA_OK : CTRLORA_ERR_CUDA;
+}
+
+// Persistent GEMM grids use at most `limit` SMs (0 = all).  A communication kernel that runs next to the backward (the
+// overlapped gradient all-reduce) owns a few SMs; a 148-CTA persistent grid would otherwise wait for them and run a second,
+// nearly empty wave.  The limit is read at launch time, i.e. it is baked into a CUDA graph at capture.
+extern "C" int ctrlora_set_sm_limit(int limit) {
+    if (limit < 0) return CTRLORA_ERR_ARG;
+    g_sm_limit = limit;
+    return CTRLORA_OK;
 }

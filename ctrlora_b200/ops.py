@@ -785,3 +785,8 @@ def conv_dgrad_weight(w16):
     _count()
     check(_lib.load().ctrlora_conv_dgrad_weight_f16(_dp(w16), _dp(out), co, taps, ci, _sp()), "conv_dgrad_weight")
     return out
+
+
+def set_sm_limit(limit):
+    """persistent GEMM grids use at most `limit` SMs (0 = all); baked into CUDA graphs at capture"""
+    check(_lib.load().ctrlora_set_sm_limit(int(limit)), "set_sm_limit")

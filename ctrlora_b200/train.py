@@ -771,6 +771,10 @@ class FinetuneTrainer:
         the stage (a block's zero-conv travels with its block); "final" is the rest: input_blocks.0-2 with their zero-convs and
         the time-embedding MLP -- ~4 M of the 36.9 M elements, the only part whose all-reduce cannot overlap the backward."""
         def stage_of(n):
+            # the ResBlocks' emb_layers (and their LoRA layers) get their gradients from emb_mlp_backward, AFTER the last
+            # block: they travel in the final bucket whatever block they sit in
+            if ".emb_layers." in n:
+                return "final"
             # zero_convs.i is differentiated right before input_blocks.i, middle_block_out right before middle_block
             if n.startswith(("middle_block.", "middle_block_out.")):
                 return "middle"
@@ -1028,9 +1032,33 @@ class PretrainTrainer(FinetuneTrainer):
 
     # -- one CUDA graph per task (the attached LoRA set is baked into the captured kernels' pointers); the graphs share one
     # memory pool: only one of them is ever in flight
+    def _overlap_cuts(self):
+        """Backward stages that close a bucket whose all-reduce then runs under the rest of the backward
+        (CTRLORA_PRETRAIN_ALLREDUCE_CUTS, default all four: middle,ib9,ib6,ib3; empty = one exchange after the backward).
+        The dense gradient buffer is 1.5 GB; measured on 2 x B200 (profiles/r2_scaling_experiments.txt): one exchange after
+        the backward 53.2 ms/step, cuts ib9 52.6, ib9+ib6 52.1-52.7, all four 52.0 -- about a third of the 3.4 ms exchange is
+        hidden; the rest is lost to the collective's CTAs and HBM traffic competing with the backward it overlaps."""
+        import os
+        cuts = getattr(self, "allreduce_cuts", None)
+        if cuts is None:
+            cuts = os.environ.get("CTRLORA_PRETRAIN_ALLREDUCE_CUTS", "middle,ib9,ib6,ib3")
+        if isinstance(cuts, str):
+            cuts = [c for c in cuts.split(",") if c]
+        return [c for c in ("middle", "ib9", "ib6", "ib3") if c in cuts]
+
+    def _cuts(self):
+        return self._overlap_cuts()
+
+    @staticmethod
+    def _sm_reserve():
+        """SMs left to the collective's CTAs while it overlaps the backward (persistent GEMM grids shrink by this much)"""
+        import os
+        return int(os.environ.get("CTRLORA_OVERLAP_SM_RESERVE", "16"))
+
     def capture(self, x0, hint_latent, context, t, noise, tasks=None, warmup=2):
         if self._static is None:
             self._static = [v.clone() for v in (x0, hint_latent, context, t, noise)]
+        overlap = self.world > 1 and bool(self._overlap_cuts())
         for task in (tasks or self.tasks or [None]):
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -1041,6 +1069,46 @@ class PretrainTrainer(FinetuneTrainer):
             cur.wait_stream(side)
             torch.cuda.synchronize()
             prepare.bump_train_version()
+            if overlap:
+                # one graph per gradient bucket (shared pool): replay k, start bucket k's all-reduce on the communication
+                # stream, replay k+1 ... (NCCL stays outside the captures).  Segments after the first cut run next to a
+                # collective: their persistent GEMM grids leave `_sm_reserve()` SMs to it.
+                buckets = dict(self.merged_buckets())
+                segs, state = [], {}
+                stream = torch.cuda.Stream()
+                stream.wait_stream(cur)
+                with torch.cuda.stream(stream):
+                    state["g"] = torch.cuda.CUDAGraph()
+                    if self._pool is None:
+                        state["g"].capture_begin()
+                    else:
+                        state["g"].capture_begin(pool=self._pool)
+
+                    def on_stage(name):
+                        if name not in buckets:
+                            return  # not an active cut
+                        state["g"].capture_end()
+                        if self._pool is None:
+                            self._pool = state["g"].pool()
+                        segs.append((state["g"], buckets[name]))
+                        ops.set_sm_limit(max(2, torch.cuda.get_device_properties(self.G.flat_p.device).multi_processor_count
+                                             - self._sm_reserve()))
+                        state["g"] = torch.cuda.CUDAGraph()
+                        state["g"].capture_begin(pool=self._pool)
+
+                    self._on_stage = on_stage
+                    try:
+                        self._static_loss[task] = self.loss_and_grads(*self._static, task=task)
+                    finally:
+                        self._on_stage = None
+                        ops.set_sm_limit(0)
+                    state["g"].capture_end()
+                    if self._pool is None:
+                        self._pool = state["g"].pool()
+                    segs.append((state["g"], buckets["final"]))
+                cur.wait_stream(stream)
+                self._graphs[task] = (segs, self._scale_used)
+                continue
             g = torch.cuda.CUDAGraph()
             kw = {} if self._pool is None else {"pool": self._pool}
             with torch.cuda.graph(g, **kw):
@@ -1070,6 +1138,8 @@ class PretrainTrainer(FinetuneTrainer):
 
     def step(self, x0, hint_latent, context, t, noise, task=None):
         task = task if task is not None else self.task
+        segs = self.segments_for(task)  # (ranks exchange their task index first: known before the backward starts)
+        overlapped = False
         if task in self._graphs:
             for dst, src in zip(self._static, (x0, hint_latent, context, t, noise)):
                 if dst.data_ptr() != src.data_ptr():
@@ -1078,12 +1148,24 @@ class PretrainTrainer(FinetuneTrainer):
                 self.cn.switch_lora(task)  # host-side pointers follow the graph (weight caches are keyed on them)
                 self.task = task
             g, self._scale_used = self._graphs[task]
-            g.replay()
+            if isinstance(g, list):
+                # bucketed exchange: the LoRA sets live in the last bucket; only the sets some rank trained are reduced
+                base_end = self.layout["base"][1]
+                lora = [(off, n) for off, n, key in segs if key != "base"]
+                for graph, ranges in g:
+                    graph.replay()
+                    self._reduce_ranges([(off, min(n, base_end - off)) for off, n in ranges if off < base_end] +
+                                        (lora if ranges is g[-1][1] else []))
+                overlapped = True
+            else:
+                g.replay()
             loss = self._static_loss[task]
         else:
             loss = self.loss_and_grads(x0, hint_latent, context, t, noise, task=task)
-        segs = self.segments_for(task)
-        self.reduce_gradients(segs)
+        if overlapped:
+            torch.cuda.current_stream().wait_stream(self._comm)  # every bucket reduced before the overflow check / AdamW
+        else:
+            self.reduce_gradients(segs)
         for off, n, _ in segs:
             ops.nonfinite_flag(self.G.flat_g[off:off + n], self.overflow_flag)
         G = self.G

@@ -128,3 +128,47 @@ def test_full_parameter_finetune_is_refused_by_the_lora_sink_and_served_by_the_d
     cn = cn.cuda()
     with pytest.raises(NotImplementedError):
         GradSink(cn)
+
+
+@pytest.mark.parametrize("kind", ["pretrain", "finetune"])
+def test_gradient_buckets_are_final_when_their_stage_fires(setup, kind):
+    """The overlapped exchange starts a bucket's all-reduce when the backward reaches its stage: every gradient of the
+    bucket must already hold its final value then (single GPU: snapshot at the stage, compare after the backward).  The
+    ResBlocks' emb_layers are differentiated after the last block and therefore belong to the final bucket."""
+    g, model, trainer, d = setup
+    if kind == "finetune":
+        from ctrlora_b200 import dropin
+        dropin.activate()
+        from cldm.model import create_model
+        from ctrlora_b200.train import FinetuneTrainer
+        from oracle import synth
+        g2 = torch.load(os.path.join(GOLD, "tiny_finetune_golden.pt"), weights_only=False)
+        m2 = create_model(os.path.join(GOLD, "tiny_finetune.yaml"), init_weights=False)
+        m2.control_model.load_state_dict(synth.synth_state_dict(g2["control_shapes"], g2["seed"], "control_model."))
+        m2.model.diffusion_model.load_state_dict(synth.synth_state_dict(g2["unet_shapes"], g2["seed"], "model.diffusion_model."))
+        trainer = FinetuneTrainer(m2.cuda().eval(), lr=1e-3)
+    trainer.allreduce_cuts = "middle,ib9,ib6,ib3"
+    buckets = dict(trainer.merged_buckets())
+    assert set(buckets) == {"middle", "ib9", "ib6", "ib3", "final"}
+    covered = sorted(r for rs in buckets.values() for r in rs)
+    assert sum(n for _, n in covered) == trainer.G.numel and all(a[0] + a[1] <= b[0] for a, b in zip(covered, covered[1:]))
+    snaps = {}
+
+    def on_stage(name):
+        snaps[name] = [trainer.G.flat_g[off:off + n].clone() for off, n in buckets[name]]
+
+    trainer._on_stage = on_stage
+    try:
+        args = (d["x0"], d["hint"], d["ctx"], d["t"], d["noise"])
+        trainer.loss_and_grads(*args, task="depth") if kind == "pretrain" else trainer.loss_and_grads(*args)
+    finally:
+        trainer._on_stage = None
+        trainer.allreduce_cuts = None
+    torch.cuda.synchronize()
+    assert set(snaps) == {"middle", "ib9", "ib6", "ib3"}
+    for name, tensors in snaps.items():
+        nonzero = 0
+        for (off, n), snap in zip(buckets[name], tensors):
+            assert torch.equal(snap, trainer.G.flat_g[off:off + n]), f"bucket {name} changed after its stage"
+            nonzero += int(snap.abs().sum().item() > 0)
+        assert nonzero > 0, f"bucket {name} was still empty at its stage"
