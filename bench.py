@@ -355,12 +355,14 @@ def run_train(args, rank, local_rank, world, device):
     ms_dev, ms_e2e = t.tolist()
     peak_tf, _, peak_src = measured_peaks()
     ips = world * B * args.steps / (ms_dev / 1e3)
+    spread = replica_spread(trainer, world)
     return {"metric": "train_images_per_sec", "value": ips, "unit": f"images/s (512x512, rank {lora_rank})", "batch_per_gpu": B,
             "lora_rank": lora_rank,
             "ms_per_step": ms_dev / args.steps, "loss": float(loss_host.item()),
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "allreduce_bytes_per_step": trainer.G.numel * 4 if world > 1 else 0, "trainable_params": trainer.G.numel,
+            "replica_param_spread": spread,
             "roofline": {"bound": "tensor", "achieved": ips / world * TF_PER_IMAGE_TRAIN, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ips / world * TF_PER_IMAGE_TRAIN / peak_tf, "peak_source": peak_src,
                          "note": "algorithmically necessary 2.11 TFLOP/image (no recompute, no frozen weight grads)"}}
@@ -437,17 +439,32 @@ def run_pretrain(args, rank, local_rank, world, device):
     peak_tf, _, peak_src = measured_peaks()
     ips = world * B * args.steps / (ms_dev / 1e3)
     lay = trainer.layout
+    spread = replica_spread(trainer, world)
     return {"metric": "pretrain_images_per_sec", "value": ips, "unit": "images/s (512x512, 9 tasks, rank 128)",
             "batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms_dev / args.steps, "loss": float(loss_host.item()),
             "tasks": len(trainer.tasks), "skipped_steps": trainer.skipped_steps,
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
-            "trainable_params": trainer.G.numel, "controlnet_params": lay["base"][1],
+            "trainable_params": trainer.G.numel, "controlnet_params": lay["base"][1], "replica_param_spread": spread,
+            "allreduce_cuts": trainer._overlap_cuts() if world > 1 else [],
             "allreduce_bytes_per_step": (4 * (lay["base"][1] + min(world, len(trainer.tasks)) * lay["lora"][trainer.tasks[0]][1])
                                          if world > 1 else 0),
             "roofline": {"bound": "tensor", "achieved": ips / world * TF_PER_IMAGE_PRETRAIN, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": ips / world * TF_PER_IMAGE_PRETRAIN / peak_tf, "peak_source": peak_src,
                          "note": "algorithmically necessary 2.33 TFLOP/image (finetune step + dense ControlNet weight gradients)"}}
+
+
+def replica_spread(trainer, world):
+    """max over the flat parameter buffer of |p_rank - p_rank0|: data-parallel replicas must stay bit-identical (every
+    gradient element reduced exactly once before AdamW); 0.0 expected, None on one GPU"""
+    if world <= 1:
+        return None
+    import torch.distributed as dist
+    ref = trainer.G.flat_p.clone()
+    dist.broadcast(ref, src=0)
+    d = (trainer.G.flat_p - ref).abs().max()
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    return float(d.item())
 
 
 def attention_roofline(device, batch=2 * BATCH, heads=8, n=LATENT * LATENT, d=40, reps=20):
