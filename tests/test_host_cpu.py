@@ -157,3 +157,29 @@ def test_product_fails_loudly_without_gpu(tiny_model):
     with pytest.raises(Exception) as e:
         tiny_model.apply_model(x, torch.tensor([1]), {"c_crossattn": [torch.zeros(1, 77, 64)], "c_concat": [x]})
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+def test_style_variant_state_dict_matches_reference():
+    """IP-Adapter / style variant (cldm/cldm_style.py, ldm/modules/attention_ip.py): the UNet's state dict has the
+    reference's keys, shapes and ORDER (`ip_scale` buffer before the attention's children, to_k_ip / to_v_ip between to_v
+    and to_out), the ControlNet is the plain inference one, and a [text, ip] context fails loudly without a GPU."""
+    from ctrlora_b200 import dropin
+    dropin.activate()
+    from cldm.model import create_model
+    g = torch.load(os.path.join(GOLD, "tiny_style_golden.pt"), weights_only=False)
+    model = create_model(os.path.join(GOLD, "tiny_style.yaml"), init_weights=False)
+    unet_sd = model.model.diffusion_model.state_dict()
+    assert list(unet_sd.keys()) == g["unet_key_order"]
+    assert {k: tuple(v.shape) for k, v in unet_sd.items()} == g["unet_shapes"]
+    assert {k: tuple(v.shape) for k, v in model.control_model.state_dict().items()} == g["control_shapes"]
+    ip_keys = [k for k in unet_sd if k.endswith("ip_scale")]
+    assert ip_keys == g["ip_scale_keys"] and len(ip_keys) == 16
+    assert not any("_ip" in k for k in model.control_model.state_dict())
+    from ldm.modules.attention_ip import IPCrossAttention
+    n_ip = sum(isinstance(m, IPCrossAttention) for m in model.model.diffusion_model.modules())
+    assert n_ip == 16  # every attn2 of the UNet, no attn1
+    if not torch.cuda.is_available():
+        x = torch.zeros(1, 4, 16, 16)
+        with pytest.raises(Exception):
+            model.apply_model(x, torch.tensor([1]), {"c_crossattn": [torch.zeros(1, 77, 64)], "c_concat": [x],
+                                                    "c_ip": [torch.zeros(1, 4, 64)]})
