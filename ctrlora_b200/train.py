@@ -1129,6 +1129,18 @@ class PretrainTrainer(FinetuneTrainer):
     def segments_for(self, task):
         return active_segments(self.layout, self._tasks_on_ranks(task)) if self.tasks else [(0, self.G.numel, "base")]
 
+    def exchange_plan(self, segs, bucket_ranges):
+        """Ranges to all-reduce after each backward bucket: the bucket's part of the ControlNet segment; the LoRA sets live
+        behind it in the flat buffer and travel with the LAST bucket, and only the sets some rank trained this step (`segs`,
+        from segments_for) are exchanged.  Every element of `segs` appears exactly once in the plan."""
+        base_end = self.layout["base"][1]
+        lora = [(off, n) for off, n, key in segs if key != "base"]
+        plan = []
+        for i, ranges in enumerate(bucket_ranges):
+            r = [(off, min(n, base_end - off)) for off, n in ranges if off < base_end]
+            plan.append(r + lora if i == len(bucket_ranges) - 1 else r)
+        return plan
+
     def reduce_gradients(self, segs=None):
         """The exchange step: all-reduce (SUM) of the ControlNet segment and of every LoRA set some rank trained this step
         (the reference's DDP reduces all 589 M elements every step; unused sets are all-zero there)."""
@@ -1149,13 +1161,9 @@ class PretrainTrainer(FinetuneTrainer):
                 self.task = task
             g, self._scale_used = self._graphs[task]
             if isinstance(g, list):
-                # bucketed exchange: the LoRA sets live in the last bucket; only the sets some rank trained are reduced
-                base_end = self.layout["base"][1]
-                lora = [(off, n) for off, n, key in segs if key != "base"]
-                for graph, ranges in g:
+                for (graph, _), ranges in zip(g, self.exchange_plan(segs, [r for _, r in g])):
                     graph.replay()
-                    self._reduce_ranges([(off, min(n, base_end - off)) for off, n in ranges if off < base_end] +
-                                        (lora if ranges is g[-1][1] else []))
+                    self._reduce_ranges(ranges)
                 overlapped = True
             else:
                 g.replay()

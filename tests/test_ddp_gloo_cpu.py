@@ -89,6 +89,22 @@ def _pretrain_worker(rank, world, port, q):
         d_off, d_n = trainer.layout["lora"]["depth"]
         untouched = torch.equal(G.flat_g[d_off:d_off + d_n], mine[d_off:d_off + d_n])
         covered = sum(n for _, n, _ in segs) + d_n == G.numel
+        # the bucketed (overlapped) exchange reduces exactly the same elements, once each, in backward order
+        trainer.allreduce_cuts = "middle,ib9,ib6,ib3"
+        merged = trainer.merged_buckets()
+        plan = trainer.exchange_plan(segs, [r for _, r in merged])
+        flat = sorted(r for ranges in plan for r in ranges)
+        want = sorted((off, n) for off, n, _ in segs)
+        disjoint = all(a[0] + a[1] <= b[0] for a, b in zip(flat, flat[1:]))
+        same_cover = sum(n for _, n in flat) == sum(n for _, n in want) and flat[0][0] == 0 and \
+            all(any(w[0] <= off and off + n <= w[0] + w[1] for w in want) for off, n in flat)
+        G.flat_g.copy_(mine)
+        for ranges in plan:
+            for off, n in ranges:
+                dist.all_reduce(G.flat_g[off:off + n])
+        bucketed_ok = all(torch.allclose(G.flat_g[off:off + n], total[off:off + n], atol=1e-6) for off, n, _ in segs) and \
+            torch.equal(G.flat_g[d_off:d_off + d_n], mine[d_off:d_off + d_n])
+        covered = covered and disjoint and same_cover and bucketed_ok and [st for st, _ in merged][-1] == "final" and len(plan) == 5
         q.put((rank, synced, keys, ok, untouched, covered))
     finally:
         dist.destroy_process_group()
